@@ -1,0 +1,195 @@
+/*
+ * limovelo_b200.h — C ABI of liblimovelo_b200.so
+ *
+ * B200-native (sm_100a) implementation of LIMO-Velo's per-sweep localization hot path:
+ * Localizator::correct -> IKFoM update_iterated_dyn_share_modified -> per iteration
+ * Mapper::match (exact 5-NN, plane fit, gates) -> Localizator::calculate_H -> HtH / Hth ->
+ * 23-DoF state update.  Plain pointers and sizes only; no torch / Eigen / ROS types.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * LIMO-Velo source tree; esekfom.hpp = include/IKFoM/IKFoM_toolkit/esekfom/esekfom.hpp).
+ * INTEGRATION.md shows the reference-side glue (the h_share_model / Localizator / Mapper
+ * call sites that would bind these).
+ *
+ * Threading: like the reference (single main thread, main.cpp:52-130) a handle is not
+ * re-entrant.  Handles are independent of each other: one handle = one sequence = one
+ * CUDA device + stream.
+ *
+ * There is NO CPU fallback: every compute entry point returns LV_ERR_CUDA when no CUDA
+ * device is usable.
+ */
+#ifndef LIMOVELO_B200_H_
+#define LIMOVELO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LV_STATE_LEN 26   /* flat state_ikfom, see lv_state_layout below                    */
+#define LV_DOF 23         /* state_ikfom::DOF (use-ikfom.hpp:12-21)                         */
+#define LV_MEAS_COLS 12   /* non-zero Jacobian columns (Localizator.cpp:31, esekfom.hpp:1647) */
+#define LV_MAX_EVALS 8    /* capacity of the per-update log: MAX_NUM_ITERS + 1 <= 8          */
+
+typedef struct lv_context* lv_handle;
+
+typedef enum lv_status {
+    LV_OK = 0,
+    LV_EMPTY_MAP = 1,          /* Localizator.cpp:24 / Mapper.cpp:42 silent returns           */
+    LV_TOO_FEW_MATCHES = 2,    /* Nm < 23: esekfom.hpp:1701-1709 branch (undefined in the ref) */
+    LV_ERR_ARG = 3,
+    LV_ERR_CUDA = 4,           /* no device / CUDA failure (see lv_last_error)                */
+    LV_ERR_CAPACITY = 5,       /* more points than the handle was created for                 */
+    LV_ERR_IO = 6              /* YAML file unreadable                                        */
+} lv_status;
+
+/*
+ * Flat state layout (26 doubles), field order of state_ikfom (use-ikfom.hpp:12-21),
+ * quaternions in Eigen coeffs() order (x, y, z, w):
+ *   [0:3) pos   [3:7) rot   [7:11) offset_R_L_I   [11:14) offset_T_L_I
+ *   [14:17) vel [17:20) bg  [20:23) ba            [23:26) grav (S2, |grav| = 9.809)
+ * Covariance P is 23 x 23 row-major in DOF order pos0 rot3 offR6 offT9 vel12 bg15 ba18 grav21.
+ */
+
+/* Configuration.  Upper-case / ROS-style names are the YAML keys read by fill_config
+ * (src/main.cpp:135-176) with the same defaults; the last block is device tuning that has
+ * no counterpart in the reference.                                                         */
+typedef struct lv_params {
+    /* Localizator */
+    int32_t MAX_NUM_ITERS;            /* main.cpp:144, default 3                           */
+    int32_t NUM_MATCH_POINTS;         /* main.cpp:146, must be 5                           */
+    int32_t estimate_extrinsics;      /* main.cpp:139                                      */
+    int32_t print_degeneracy_values;  /* main.cpp:156 (eigenvalues are returned in the log) */
+    double MAX_DIST_PLANE;            /* main.cpp:148, default 2.0                         */
+    float PLANES_THRESHOLD;           /* main.cpp:149, default 0.1                         */
+    float pad0_;
+    double LiDAR_noise;               /* main.cpp:152 -> R                                 */
+    double degeneracy_threshold;      /* main.cpp:155 -> D                                 */
+    double LIMITS[LV_DOF];            /* main.cpp:145, default 23 x 0.001                  */
+    /* IMU process noise (Localizator.cpp:164-168) */
+    double covariance_gyroscope, covariance_acceleration;
+    double covariance_bias_gyroscope, covariance_bias_acceleration;
+    /* extrinsics / gravity (Localizator.cpp:135-153) */
+    float initial_gravity[3];
+    float I_Translation_L[3];
+    float I_Rotation_L[9];            /* row-major YAML list                               */
+    float map_downsample_size;        /* ikd-Tree box_length, Mapper.cpp:65 = 0.2          */
+    /* ---- device tuning (not in the reference) ---- */
+    float voxel_size;                 /* edge of the hashed search voxels [m], default 0.5 */
+    int32_t device;                   /* CUDA device ordinal                               */
+    int32_t sort_queries;             /* 1: reorder the sweep by voxel key once per update */
+    int64_t max_map_points;           /* capacity of the device map                        */
+    int64_t max_points;               /* capacity of one sweep                             */
+    void* stream;                     /* cudaStream_t to run on; NULL = own stream         */
+} lv_params;
+
+/* One record per h-evaluation of update_iterated_dyn_share_modified (esekfom.hpp:1634-1822) */
+typedef struct lv_iter_log {
+    int64_t n_matches;        /* Nm = rows of h_x (esekfom.hpp:1650)                       */
+    int32_t converged;        /* dyn_share.converge after esekfom.hpp:1748-1762            */
+    int32_t degenerate;       /* 1 if any eigenvalue of HTH[0:6,0:6] < D (esekfom.hpp:1740) */
+    double HTH[144];          /* row-major 12 x 12 (esekfom.hpp:1723)                      */
+    double HTh[12];           /* h_x^T h (esekfom.hpp:1727)                                */
+    double dx[LV_DOF];        /* dx_ before the degeneracy mask (esekfom.hpp:1733)         */
+    double x_after[LV_STATE_LEN];
+} lv_iter_log;
+
+typedef struct lv_profile {
+    double measure_ms;        /* sum of device time of the fused measure kernel            */
+    double solve_ms;          /* sum of device time of the IESKF step kernel               */
+    double build_ms;          /* sum of device time of map (re)builds                      */
+    int64_t measure_launches, solve_launches, build_launches;
+    int64_t total_launches;   /* every kernel launched by this handle since the last reset */
+} lv_profile;
+
+/* ------------------------------------------------------------------------------------------ */
+/* configuration                                                                              */
+void lv_default_params(lv_params* p);                         /* defaults of main.cpp:137-175 */
+lv_status lv_params_from_yaml(const char* path, lv_params* p); /* config/<name>.yaml keys           */
+
+/* lifetime: replaces the Localizator / Mapper singletons (Localizator.cpp:100-103,
+ * Mapper.hpp:35-38): one handle owns one filter and one map.                                */
+lv_status lv_create(const lv_params* p, lv_handle* out);
+void lv_destroy(lv_handle h);
+const char* lv_last_error(void);
+const char* lv_version(void);
+
+/* ---- Mapper boundary (include/Headers/Mapper.hpp:17-23) ---------------------------------- */
+/* Mapper::add on an empty map == KD_TREE::Build, no downsampling (Mapper.cpp:26,68-71).      */
+lv_status lv_map_build(lv_handle h, const float* xyz, int64_t m);
+/* Mapper::add on an existing map == KD_TREE::Add_Points (Mapper.cpp:73-76,
+ * ikd_Tree.cpp:478-573): 0.2 m voxel rule when downsample != 0.                              */
+lv_status lv_map_add(lv_handle h, const float* xyz, int64_t n, int downsample);
+int64_t lv_map_size(lv_handle h);                             /* Mapper::size  (Mapper.cpp:32) */
+int lv_map_exists(lv_handle h);                               /* Mapper::exists (Mapper.cpp:36) */
+int64_t lv_map_points(lv_handle h, float* xyz_out, int64_t cap); /* KD_TREE::flatten            */
+/* same as lv_map_build but xyz is a DEVICE pointer (data already resident in HBM)            */
+lv_status lv_map_build_device(lv_handle h, const float* d_xyz, int64_t m);
+
+/* ---- operator boundary: the measurement model IKFoM calls (esekfom.hpp:128,1637) --------- */
+/* compat mode: fills h_x (Nm x 12, COLUMN-major like Eigen::MatrixXd) and h (Nm) exactly as
+ * IKFoM::h_share_model does (use-ikfom.cpp:16-37); rows in input-point order.                */
+lv_status lv_measure(lv_handle h, const double* x /*LV_STATE_LEN*/, const float* xyz_lidar, int64_t n,
+                     double* h_x, double* h_vec, int64_t* nm);
+/* fast mode: what update_iterated_dyn_share_modified consumes when Nm >= 23
+ * (esekfom.hpp:1722-1729): HTH = h_x^T h_x (row-major 12x12), HTh = h_x^T h.                 */
+lv_status lv_measure_reduced(lv_handle h, const double* x, const float* xyz_lidar, int64_t n,
+                             double* HTH, double* HTh, int64_t* nm);
+/* Mapper::match without the compaction (Mapper.cpp:40-56): per input point the world point,
+ * the 5 neighbours (indices into the current map order of lv_map_points, squared distances
+ * ascending), the fitted plane (A,B,C,D), the point-to-plane distance and is_chosen().
+ * Any output pointer may be NULL.  Neighbour data are defined for points whose 5th
+ * neighbour is closer than MAX_DIST_PLANE (others report idx -1).                            */
+lv_status lv_match_all(lv_handle h, const double* x, const float* xyz_lidar, int64_t n,
+                       uint8_t* valid, int32_t* nn_idx, float* nn_sqd, float* plane, float* dist,
+                       float* g_world);
+
+/* ---- module boundary: Localizator (include/Headers/Localizator.hpp:24-33) ---------------- */
+lv_status lv_set_state(lv_handle h, const double* x, const double* P);   /* change_x / change_P */
+lv_status lv_get_state(lv_handle h, double* x, double* P);               /* get_x / get_P       */
+/* Localizator::init_IKFoM_state (Localizator.cpp:135-153); q_imu = (x,y,z,w)                 */
+lv_status lv_init_state(lv_handle h, const float q_imu[4]);
+/* Localizator::propagate -> esekf::predict (Localizator.cpp:159-173, esekfom.hpp:279-384)    */
+lv_status lv_predict(lv_handle h, const double acc[3], const double gyro[3], double dt);
+/* Localizator::correct(points, time) (Localizator.cpp:23-27): the whole iterated update.
+ * xyz_lidar: HOST buffer of n deskewed points in the LiDAR frame.  logs (capacity
+ * LV_MAX_EVALS) / n_evals / x_out / P_out may be NULL.                                       */
+lv_status lv_correct(lv_handle h, const float* xyz_lidar, int64_t n, double time,
+                     lv_iter_log* logs, int32_t* n_evals, double* x_out, double* P_out);
+/* same, but the points are already resident in HBM (DEVICE pointer) and nothing is copied
+ * back except through lv_get_state / lv_last_logs.                                           */
+lv_status lv_correct_device(lv_handle h, const float* d_xyz_lidar, int64_t n, double time);
+lv_status lv_last_logs(lv_handle h, lv_iter_log* logs, int32_t* n_evals);
+double lv_last_time_updated(lv_handle h);                     /* Localizator::last_time_updated */
+
+/* ---- utilities --------------------------------------------------------------------------- */
+void* lv_host_alloc(int64_t bytes);                           /* pinned host memory            */
+void lv_host_free(void* p);
+void* lv_device_alloc(lv_handle h, int64_t bytes);
+void lv_device_free(lv_handle h, void* p);
+lv_status lv_memcpy_h2d(lv_handle h, void* dst, const void* src, int64_t bytes);
+lv_status lv_synchronize(lv_handle h);
+lv_status lv_profile_enable(lv_handle h, int on);             /* CUDA-event timing per kernel  */
+lv_status lv_profile_get(lv_handle h, lv_profile* out, int reset);
+lv_status lv_flush_l2(lv_handle h);                           /* writes a 256 MiB scratch      */
+
+/* ---- synthetic reader (replaces the ROS subscribers of src/main.cpp:27-39) ---- */
+typedef struct lv_synth_world lv_synth_world;
+/* seeded "city-block" world whose surface sampling holds exactly m map points              */
+lv_synth_world* lv_synth_world_create(uint64_t seed, int64_t m);
+void lv_synth_world_destroy(lv_synth_world* w);
+int64_t lv_synth_world_map(const lv_synth_world* w, float* xyz_out, int64_t cap);
+double lv_synth_world_extent(const lv_synth_world* w);
+/* pose of the sensor platform at arc-length s along the world's road (state layout above)   */
+void lv_synth_pose(const lv_synth_world* w, double s, const lv_params* p, double* x_out);
+/* ray-cast one sweep of `rings` x `azimuths` beams (elevations elev_lo..elev_hi degrees)
+ * from state x; writes exactly rings*azimuths points in the LiDAR frame, firing order.       */
+int64_t lv_synth_sweep(const lv_synth_world* w, const double* x, int rings, int azimuths,
+                       double elev_lo_deg, double elev_hi_deg, double min_dist, double range_sigma,
+                       uint64_t seed, float* xyz_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIMOVELO_B200_H_ */

@@ -1,0 +1,380 @@
+"""limovelo_b200 — Python (ctypes) access to liblimovelo_b200.so for tests and benchmarks.
+
+The product is the C-ABI shared library (include/limovelo_b200.h) built from csrc/ (CUDA, sm_100a)
+and host/ (C++); this module only marshals numpy arrays into it.  There is no Python or CPU
+implementation behind it: if the library is missing, loading raises, and without a CUDA device
+every compute call returns LV_ERR_CUDA (raised as RuntimeError here).
+
+The directory name contains a hyphen, so import it through `__graft_entry__.load_package()`
+(registers it as module `limovelo_b200`).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblimovelo_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "limovelo_b200.h")
+
+STATE_LEN, DOF, MAX_EVALS = 26, 23, 8
+OK, EMPTY_MAP, TOO_FEW_MATCHES, ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_IO = range(7)
+STATUS_NAMES = ["LV_OK", "LV_EMPTY_MAP", "LV_TOO_FEW_MATCHES", "LV_ERR_ARG", "LV_ERR_CUDA", "LV_ERR_CAPACITY",
+                "LV_ERR_IO"]
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("MAX_NUM_ITERS", C.c_int32), ("NUM_MATCH_POINTS", C.c_int32), ("estimate_extrinsics", C.c_int32),
+        ("print_degeneracy_values", C.c_int32), ("MAX_DIST_PLANE", C.c_double), ("PLANES_THRESHOLD", C.c_float),
+        ("pad0_", C.c_float), ("LiDAR_noise", C.c_double), ("degeneracy_threshold", C.c_double),
+        ("LIMITS", C.c_double * DOF),
+        ("covariance_gyroscope", C.c_double), ("covariance_acceleration", C.c_double),
+        ("covariance_bias_gyroscope", C.c_double), ("covariance_bias_acceleration", C.c_double),
+        ("initial_gravity", C.c_float * 3), ("I_Translation_L", C.c_float * 3), ("I_Rotation_L", C.c_float * 9),
+        ("map_downsample_size", C.c_float), ("voxel_size", C.c_float), ("device", C.c_int32),
+        ("sort_queries", C.c_int32), ("max_map_points", C.c_int64), ("max_points", C.c_int64),
+        ("stream", C.c_void_p),
+    ]
+
+
+class IterLog(C.Structure):
+    _fields_ = [("n_matches", C.c_int64), ("converged", C.c_int32), ("degenerate", C.c_int32),
+                ("HTH", C.c_double * 144), ("HTh", C.c_double * 12), ("dx", C.c_double * DOF),
+                ("x_after", C.c_double * STATE_LEN)]
+
+
+class Profile(C.Structure):
+    _fields_ = [("measure_ms", C.c_double), ("solve_ms", C.c_double), ("build_ms", C.c_double),
+                ("measure_launches", C.c_int64), ("solve_launches", C.c_int64), ("build_launches", C.c_int64),
+                ("total_launches", C.c_int64)]
+
+
+def build(verbose=False):
+    """Compile liblimovelo_b200.so in-tree with nvcc for sm_100a (works without a GPU)."""
+    cmd = ["make", "-C", _HERE, "-j8"]
+    if not verbose:
+        cmd.insert(1, "-s")
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("liblimovelo_b200.so is not built (run __graft_entry__.build()); there is no fallback")
+    L = C.CDLL(LIB_PATH)
+    dp, fp, vp = C.POINTER(C.c_double), C.POINTER(C.c_float), C.c_void_p
+    i64, i32p = C.c_int64, C.POINTER(C.c_int32)
+    L.lv_default_params.argtypes = [C.POINTER(Params)]
+    L.lv_default_params.restype = None
+    L.lv_params_from_yaml.argtypes = [C.c_char_p, C.POINTER(Params)]
+    L.lv_create.argtypes = [C.POINTER(Params), C.POINTER(vp)]
+    L.lv_destroy.argtypes = [vp]
+    L.lv_destroy.restype = None
+    L.lv_last_error.restype = C.c_char_p
+    L.lv_version.restype = C.c_char_p
+    L.lv_map_build.argtypes = [vp, fp, i64]
+    L.lv_map_add.argtypes = [vp, fp, i64, C.c_int]
+    L.lv_map_size.argtypes = [vp]
+    L.lv_map_size.restype = i64
+    L.lv_map_exists.argtypes = [vp]
+    L.lv_map_points.argtypes = [vp, fp, i64]
+    L.lv_map_points.restype = i64
+    L.lv_map_build_device.argtypes = [vp, vp, i64]
+    L.lv_measure.argtypes = [vp, dp, fp, i64, dp, dp, C.POINTER(i64)]
+    L.lv_measure_reduced.argtypes = [vp, dp, fp, i64, dp, dp, C.POINTER(i64)]
+    L.lv_match_all.argtypes = [vp, dp, fp, i64, C.POINTER(C.c_uint8), i32p, fp, fp, fp, fp]
+    L.lv_set_state.argtypes = [vp, dp, dp]
+    L.lv_get_state.argtypes = [vp, dp, dp]
+    L.lv_init_state.argtypes = [vp, fp]
+    L.lv_predict.argtypes = [vp, dp, dp, C.c_double]
+    L.lv_correct.argtypes = [vp, fp, i64, C.c_double, C.POINTER(IterLog), i32p, dp, dp]
+    L.lv_correct_device.argtypes = [vp, vp, i64, C.c_double]
+    L.lv_last_logs.argtypes = [vp, C.POINTER(IterLog), i32p]
+    L.lv_last_time_updated.argtypes = [vp]
+    L.lv_last_time_updated.restype = C.c_double
+    L.lv_host_alloc.argtypes = [i64]
+    L.lv_host_alloc.restype = vp
+    L.lv_host_free.argtypes = [vp]
+    L.lv_host_free.restype = None
+    L.lv_device_alloc.argtypes = [vp, i64]
+    L.lv_device_alloc.restype = vp
+    L.lv_device_free.argtypes = [vp, vp]
+    L.lv_device_free.restype = None
+    L.lv_memcpy_h2d.argtypes = [vp, vp, vp, i64]
+    L.lv_synchronize.argtypes = [vp]
+    L.lv_profile_enable.argtypes = [vp, C.c_int]
+    L.lv_profile_get.argtypes = [vp, C.POINTER(Profile), C.c_int]
+    L.lv_flush_l2.argtypes = [vp]
+    L.lv_synth_world_create.argtypes = [C.c_uint64, i64]
+    L.lv_synth_world_create.restype = vp
+    L.lv_synth_world_destroy.argtypes = [vp]
+    L.lv_synth_world_destroy.restype = None
+    L.lv_synth_world_map.argtypes = [vp, fp, i64]
+    L.lv_synth_world_map.restype = i64
+    L.lv_synth_world_extent.argtypes = [vp]
+    L.lv_synth_world_extent.restype = C.c_double
+    L.lv_synth_pose.argtypes = [vp, C.c_double, C.POINTER(Params), dp]
+    L.lv_synth_pose.restype = None
+    L.lv_synth_sweep.argtypes = [vp, dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                 C.c_uint64, fp]
+    L.lv_synth_sweep.restype = i64
+    _lib = L
+    return L
+
+
+def _f(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _d(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def default_params(**over):
+    p = Params()
+    lib().lv_default_params(C.byref(p))
+    for k, v in over.items():
+        cur = getattr(p, k)
+        if hasattr(cur, "__len__"):
+            for i, x in enumerate(v):
+                cur[i] = x
+        else:
+            setattr(p, k, v)
+    return p
+
+
+def params_from_yaml(path, **over):
+    p = default_params()
+    st = lib().lv_params_from_yaml(str(path).encode(), C.byref(p))
+    if st != OK:
+        raise RuntimeError("lv_params_from_yaml(%s) -> %s" % (path, STATUS_NAMES[st]))
+    for k, v in over.items():
+        setattr(p, k, v)
+    return p
+
+
+CONFIG_DIR = os.path.join(_HERE, "config")
+
+
+def _check(st, allow=()):
+    if st != OK and st not in allow:
+        raise RuntimeError("%s: %s" % (STATUS_NAMES[st], lib().lv_last_error().decode()))
+    return st
+
+
+def _logs_to_py(logs, n):
+    out = []
+    for i in range(n):
+        lg = logs[i]
+        out.append(dict(n_matches=int(lg.n_matches), converged=int(lg.converged), degenerate=int(lg.degenerate),
+                        HTH=np.array(lg.HTH[:]).reshape(12, 12), HTh=np.array(lg.HTh[:]),
+                        dx=np.array(lg.dx[:]), x_after=np.array(lg.x_after[:])))
+    return out
+
+
+class Localizer:
+    """One lv_handle: the Localizator + Mapper pair of one sequence on one GPU."""
+
+    def __init__(self, params):
+        self.L = lib()
+        self.params = params
+        self.h = C.c_void_p()
+        _check(self.L.lv_create(C.byref(params), C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.lv_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # Mapper
+    def map_build(self, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        return _check(self.L.lv_map_build(self.h, _f(xyz), xyz.shape[0]))
+
+    def map_add(self, xyz, downsample=True):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        return _check(self.L.lv_map_add(self.h, _f(xyz), xyz.shape[0], int(downsample)))
+
+    def map_size(self):
+        return int(self.L.lv_map_size(self.h))
+
+    def map_points(self):
+        n = self.map_size()
+        out = np.zeros((max(n, 1), 3), np.float32)
+        k = self.L.lv_map_points(self.h, _f(out), n)
+        return out[:k]
+
+    # operator boundary
+    def measure_reduced(self, x, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        HTH, HTh, nm = np.zeros((12, 12)), np.zeros(12), C.c_int64(0)
+        st = _check(self.L.lv_measure_reduced(self.h, _d(x), _f(xyz), xyz.shape[0], _d(HTH), _d(HTh), C.byref(nm)),
+                    allow=(EMPTY_MAP,))
+        return st, HTH, HTh, nm.value
+
+    def measure(self, x, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        n = xyz.shape[0]
+        hx, h, nm = np.zeros(12 * n), np.zeros(n), C.c_int64(0)
+        st = _check(self.L.lv_measure(self.h, _d(x), _f(xyz), n, _d(hx), _d(h), C.byref(nm)), allow=(EMPTY_MAP,))
+        k = nm.value
+        return st, hx[:12 * k].reshape(12, k).T.copy(), h[:k].copy()
+
+    def match_all(self, x, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        n = xyz.shape[0]
+        out = dict(valid=np.zeros(n, np.uint8), nn_idx=np.zeros((n, 5), np.int32), nn_sqd=np.zeros((n, 5), np.float32),
+                   plane=np.zeros((n, 4), np.float32), dist=np.zeros(n, np.float32), g=np.zeros((n, 3), np.float32))
+        st = _check(self.L.lv_match_all(self.h, _d(x), _f(xyz), n, out["valid"].ctypes.data_as(C.POINTER(C.c_uint8)),
+                                        out["nn_idx"].ctypes.data_as(C.POINTER(C.c_int32)), _f(out["nn_sqd"]),
+                                        _f(out["plane"]), _f(out["dist"]), _f(out["g"])), allow=(EMPTY_MAP,))
+        out["status"] = st
+        return out
+
+    # Localizator
+    def set_state(self, x, P):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        P = np.ascontiguousarray(P, dtype=np.float64)
+        _check(self.L.lv_set_state(self.h, _d(x), _d(P)))
+
+    def get_state(self):
+        x, P = np.zeros(STATE_LEN), np.zeros((DOF, DOF))
+        _check(self.L.lv_get_state(self.h, _d(x), _d(P)))
+        return x, P
+
+    def init_state(self, q_imu=(0, 0, 0, 1)):
+        q = np.ascontiguousarray(q_imu, dtype=np.float32)
+        _check(self.L.lv_init_state(self.h, _f(q)))
+
+    def predict(self, acc, gyro, dt):
+        acc = np.ascontiguousarray(acc, dtype=np.float64)
+        gyro = np.ascontiguousarray(gyro, dtype=np.float64)
+        _check(self.L.lv_predict(self.h, _d(acc), _d(gyro), float(dt)))
+
+    def correct(self, xyz, time=0.0, raw_ptr=None, n=None):
+        """Localizator::correct.  xyz: numpy (host) array, or raw_ptr/n for a pinned host buffer."""
+        if raw_ptr is None:
+            xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+            ptr, n = _f(xyz), xyz.shape[0]
+        else:
+            ptr = C.cast(raw_ptr, C.POINTER(C.c_float))
+        logs = (IterLog * MAX_EVALS)()
+        ne = C.c_int32(0)
+        x, P = np.zeros(STATE_LEN), np.zeros((DOF, DOF))
+        st = _check(self.L.lv_correct(self.h, ptr, n, float(time), logs, C.byref(ne), _d(x), _d(P)),
+                    allow=(EMPTY_MAP, TOO_FEW_MATCHES))
+        return st, x, P, _logs_to_py(logs, ne.value)
+
+    def correct_device(self, d_ptr, n, time=0.0):
+        return _check(self.L.lv_correct_device(self.h, d_ptr, n, float(time)), allow=(EMPTY_MAP,))
+
+    def last_logs(self):
+        logs = (IterLog * MAX_EVALS)()
+        ne = C.c_int32(0)
+        st = _check(self.L.lv_last_logs(self.h, logs, C.byref(ne)), allow=(TOO_FEW_MATCHES,))
+        return st, _logs_to_py(logs, ne.value)
+
+    # utilities
+    def device_alloc(self, nbytes):
+        p = self.L.lv_device_alloc(self.h, nbytes)
+        if not p:
+            raise RuntimeError("lv_device_alloc failed")
+        return p
+
+    def device_free(self, p):
+        self.L.lv_device_free(self.h, p)
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr)
+        p = self.device_alloc(arr.nbytes)
+        _check(self.L.lv_memcpy_h2d(self.h, p, arr.ctypes.data_as(C.c_void_p), arr.nbytes))
+        return p
+
+    def synchronize(self):
+        _check(self.L.lv_synchronize(self.h))
+
+    def profile_enable(self, on=True):
+        _check(self.L.lv_profile_enable(self.h, int(on)))
+
+    def profile(self, reset=True):
+        p = Profile()
+        _check(self.L.lv_profile_get(self.h, C.byref(p), int(reset)))
+        return {k: getattr(p, k) for k, _ in Profile._fields_}
+
+    def flush_l2(self):
+        _check(self.L.lv_flush_l2(self.h))
+
+
+class PinnedBuffer:
+    """Pinned host memory (lv_host_alloc) viewed as a numpy float32 array."""
+
+    def __init__(self, shape):
+        self.L = lib()
+        n = int(np.prod(shape))
+        self.ptr = self.L.lv_host_alloc(n * 4)
+        if not self.ptr:
+            raise RuntimeError("lv_host_alloc failed (no CUDA device?)")
+        self.array = np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(C.c_float)), shape=(n,)).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.L.lv_host_free(self.ptr)
+            self.ptr = None
+
+
+class SynthWorld:
+    """Seeded synthetic world + LiDAR ray caster (host C++, limo-velo_b200/host/lv_synth.cpp)."""
+
+    def __init__(self, seed, m):
+        self.L = lib()
+        self.w = self.L.lv_synth_world_create(int(seed), int(m))
+        if not self.w:
+            raise RuntimeError("lv_synth_world_create failed")
+        self.m = int(m)
+
+    def __del__(self):
+        try:
+            if self.w:
+                self.L.lv_synth_world_destroy(self.w)
+                self.w = None
+        except Exception:
+            pass
+
+    def map(self):
+        out = np.zeros((self.m, 3), np.float32)
+        n = self.L.lv_synth_world_map(self.w, _f(out), self.m)
+        return out[:n]
+
+    def extent(self):
+        return float(self.L.lv_synth_world_extent(self.w))
+
+    def pose(self, s, params):
+        x = np.zeros(STATE_LEN)
+        self.L.lv_synth_pose(self.w, float(s), C.byref(params), _d(x))
+        return x
+
+    def sweep(self, x, rings=64, azimuths=1024, elev=(-24.8, 2.0), min_dist=4.0, range_sigma=0.02, seed=0, out=None):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if out is None:
+            out = np.zeros((rings * azimuths, 3), np.float32)
+        n = self.L.lv_synth_sweep(self.w, _d(x), rings, azimuths, elev[0], elev[1], min_dist, range_sigma, int(seed),
+                                  _f(out))
+        assert n == rings * azimuths
+        return out

@@ -1,0 +1,540 @@
+/*
+ * lv_capi.cu — context object and the C ABI of liblimovelo_b200.so (include/limovelo_b200.h).
+ *
+ * One lv_context replaces the Localizator + Mapper singletons of the reference
+ * (src/Modules/Localizator.cpp:100-103, include/Headers/Mapper.hpp:35-38): it owns the IKFoM
+ * state mirror, the device map and the device buffers of one sequence, on one CUDA stream.
+ * No CPU fallback exists: without a usable CUDA device every compute call returns LV_ERR_CUDA.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/limovelo_b200.h"
+#include "lv_host.h"
+#include "lv_internal.h"
+
+using namespace lv;
+
+static_assert(sizeof(lv_iter_log) == sizeof(IterLog), "lv_iter_log must mirror lv::IterLog");
+static_assert(LV_MAX_EVALS == kMaxEvals, "log capacity");
+static_assert(LV_STATE_LEN == kStateLen && LV_DOF == kDof, "state layout");
+
+static thread_local std::string g_last_error;
+static void set_error(const std::string& s) { g_last_error = s; }
+
+#define LV_CUDA(call)                                                                            \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            char buf__[512];                                                                     \
+            snprintf(buf__, sizeof(buf__), "%s:%d: %s -> %s", __FILE__, __LINE__, #call,         \
+                     cudaGetErrorString(e__));                                                   \
+            set_error(buf__);                                                                    \
+            return LV_ERR_CUDA;                                                                  \
+        }                                                                                        \
+    } while (0)
+
+struct EventPair { cudaEvent_t a, b; int kind; };   /* kind 0 measure, 1 solve, 2 build */
+
+struct lv_context {
+    lv_params prm;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    MapBuffers map;
+    float* d_sweep = nullptr;          /* max_points x 3 */
+    UpdateCtrl* d_ctrl = nullptr;
+    UpdateCtrl* h_ctrl = nullptr;      /* pinned mirror for the D2H of results */
+    double* d_partials = nullptr;
+    double* d_reduced = nullptr;       /* 157 doubles */
+    double* h_reduced = nullptr;       /* pinned */
+    void* d_flush = nullptr;
+    /* per-point debug outputs (lazily allocated, max_points) */
+    uint8_t* d_valid = nullptr; int32_t* d_nn_idx = nullptr; float* d_nn_sqd = nullptr;
+    float* d_plane = nullptr; float* d_dist = nullptr; float* d_gworld = nullptr; double* d_rows = nullptr;
+    /* host mirror of the filter (get_x / get_P) */
+    double x[LV_STATE_LEN];
+    double P[LV_DOF * LV_DOF];
+    bool state_dirty = true;           /* host mirror newer than d_ctrl->x/P */
+    bool pending_fetch = false;        /* device holds results not yet mirrored (lv_correct_device) */
+    double last_time_updated = -1;
+    lv_iter_log logs[LV_MAX_EVALS];
+    int32_t n_evals = 0;
+    int32_t last_status = LV_OK;
+    /* profiling */
+    bool profile = false;
+    std::vector<EventPair> pending;
+    std::vector<EventPair> pool;
+    lv_profile prof;
+    IeskfParams iprm;
+};
+
+static lv_status drain_events(lv_context* h) {
+    if (h->pending.empty()) return LV_OK;
+    LV_CUDA(cudaStreamSynchronize(h->stream));
+    for (auto& e : h->pending) {
+        float ms = 0;
+        LV_CUDA(cudaEventElapsedTime(&ms, e.a, e.b));
+        if (e.kind == 0) { h->prof.measure_ms += ms; h->prof.measure_launches++; }
+        else if (e.kind == 1) { h->prof.solve_ms += ms; h->prof.solve_launches++; }
+        else { h->prof.build_ms += ms; h->prof.build_launches++; }
+        h->pool.push_back(e);
+    }
+    h->pending.clear();
+    return LV_OK;
+}
+static bool prof_begin(lv_context* h, int kind, EventPair* ep) {
+    if (!h->profile) return false;
+    if (h->pending.size() > 8192) drain_events(h);
+    if (h->pool.empty()) {
+        EventPair e;
+        if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return false;
+        h->pool.push_back(e);
+    }
+    *ep = h->pool.back();
+    h->pool.pop_back();
+    ep->kind = kind;
+    cudaEventRecord(ep->a, h->stream);
+    return true;
+}
+static void prof_end(lv_context* h, EventPair* ep) {
+    cudaEventRecord(ep->b, h->stream);
+    h->pending.push_back(*ep);
+}
+
+static void fill_iprm(lv_context* h) {
+    h->iprm.R = h->prm.LiDAR_noise;
+    h->iprm.D = h->prm.degeneracy_threshold;
+    for (int i = 0; i < kN; ++i) h->iprm.limits[i] = h->prm.LIMITS[i];
+    h->iprm.max_iter = h->prm.MAX_NUM_ITERS;
+    h->iprm.estimate_extrinsics = h->prm.estimate_extrinsics;
+}
+
+static MeasureArgs make_measure_args(lv_context* h, const float* d_xyz, int64_t n) {
+    MeasureArgs a;
+    memset(&a, 0, sizeof(a));
+    a.xyz = d_xyz;
+    a.n = (int32_t)n;
+    a.n_tiles = (int32_t)((n + kMeasureThreads - 1) / kMeasureThreads);
+    a.map = map_view(h->map);
+    a.ctrl = h->d_ctrl;
+    const double md = h->prm.MAX_DIST_PLANE;
+    a.gate_d2 = md * md;
+    float f = (float)a.gate_d2;
+    if ((double)f < a.gate_d2) f = nextafterf(f, INFINITY);
+    a.max_d2 = f;
+    a.max_ring = (int32_t)ceil(md / (double)h->map.cell);
+    if (a.max_ring < 1) a.max_ring = 1;
+    a.planes_threshold = h->prm.PLANES_THRESHOLD;
+    a.estimate_extrinsics = h->prm.estimate_extrinsics;
+    a.partials = h->d_partials;
+    return a;
+}
+
+template <class T>
+static cudaError_t ensure(T** p, size_t count) {
+    if (*p) return cudaSuccess;
+    return cudaMalloc(p, sizeof(T) * count);
+}
+
+extern "C" {
+
+const char* lv_last_error(void) { return g_last_error.c_str(); }
+const char* lv_version(void) { return "limovelo_b200 0.1 (sm_100a)"; }
+
+lv_status lv_create(const lv_params* p, lv_handle* out) {
+    if (!p || !out) return LV_ERR_ARG;
+    *out = nullptr;
+    if (p->NUM_MATCH_POINTS != 5) { set_error("NUM_MATCH_POINTS must be 5 (5x3 plane fit)"); return LV_ERR_ARG; }
+    if (p->MAX_NUM_ITERS < 1 || p->MAX_NUM_ITERS + 1 > LV_MAX_EVALS) { set_error("MAX_NUM_ITERS out of range"); return LV_ERR_ARG; }
+    if (!(p->voxel_size > 0.f) || p->max_map_points <= 0 || p->max_points <= 0) { set_error("bad capacity / voxel_size"); return LV_ERR_ARG; }
+    if (p->max_map_points > 0x7FFFFFF0ll || p->max_points > 0x7FFFFFF0ll) { set_error("capacity beyond 2^31 points"); return LV_ERR_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        set_error("no CUDA device available (there is no CPU fallback)");
+        return LV_ERR_CUDA;
+    }
+    LV_CUDA(cudaSetDevice(p->device));
+    lv_context* h = new lv_context();
+    h->prm = *p;
+    memset(&h->prof, 0, sizeof(h->prof));
+    memset(h->logs, 0, sizeof(h->logs));
+    fill_iprm(h);
+    if (p->stream) { h->stream = (cudaStream_t)p->stream; h->own_stream = false; }
+    else { LV_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+    MapBuffers& m = h->map;
+    memset(&m, 0, sizeof(m));
+    m.cap = p->max_map_points;
+    m.cell = p->voxel_size;
+    m.inv_cell = 1.0f / p->voxel_size;
+    uint32_t tcap = 1024;
+    while ((uint64_t)tcap < 2ull * (uint64_t)m.cap && tcap < 0x80000000u) tcap <<= 1;
+    m.table_cap = tcap;
+    m.sort_tmp_bytes = map_sort_tmp_bytes(m.cap);
+    { const size_t t2 = lvh_map_add_tmp_bytes(m.cap); if (t2 > m.sort_tmp_bytes) m.sort_tmp_bytes = t2; }
+    LV_CUDA(cudaMalloc(&m.xyz, sizeof(float) * 3 * m.cap));
+    LV_CUDA(cudaMalloc(&m.xyz_alt, sizeof(float) * 3 * m.cap));
+    LV_CUDA(cudaMalloc(&m.keys, sizeof(uint64_t) * m.cap));
+    LV_CUDA(cudaMalloc(&m.keys_sorted, sizeof(uint64_t) * m.cap));
+    LV_CUDA(cudaMalloc(&m.vals, sizeof(uint32_t) * m.cap));
+    LV_CUDA(cudaMalloc(&m.vals_sorted, sizeof(uint32_t) * m.cap));
+    LV_CUDA(cudaMalloc(&m.pts, sizeof(float4) * m.cap));
+    LV_CUDA(cudaMalloc(&m.table, sizeof(uint4) * (size_t)m.table_cap));
+    LV_CUDA(cudaMalloc(&m.counter, sizeof(uint32_t) * 4));
+    LV_CUDA(cudaMalloc(&m.sort_tmp, m.sort_tmp_bytes));
+    LV_CUDA(cudaMalloc(&h->d_sweep, sizeof(float) * 3 * p->max_points));
+    LV_CUDA(cudaMalloc(&h->d_ctrl, sizeof(UpdateCtrl)));
+    LV_CUDA(cudaMemset(h->d_ctrl, 0, sizeof(UpdateCtrl)));
+    LV_CUDA(cudaMallocHost(&h->h_ctrl, sizeof(UpdateCtrl)));
+    LV_CUDA(cudaMalloc(&h->d_partials, sizeof(double) * kPartialStride * (148 * 4 + 8)));
+    LV_CUDA(cudaMalloc(&h->d_reduced, sizeof(double) * 160));
+    LV_CUDA(cudaMallocHost(&h->h_reduced, sizeof(double) * 160));
+    /* default filter state: identity pose, P = I (esekf constructor); callers normally follow
+     * with lv_init_state or lv_set_state */
+    for (int i = 0; i < LV_STATE_LEN; ++i) h->x[i] = 0;
+    h->x[kRot + 3] = 1; h->x[kOffR + 3] = 1; h->x[kGrav] = LV_S2_LEN;
+    for (int i = 0; i < LV_DOF * LV_DOF; ++i) h->P[i] = (i % (LV_DOF + 1) == 0) ? 1.0 : 0.0;
+    *out = h;
+    return LV_OK;
+}
+
+void lv_destroy(lv_handle h) {
+    if (!h) return;
+    cudaSetDevice(h->prm.device);
+    cudaStreamSynchronize(h->stream);
+    for (auto& e : h->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (auto& e : h->pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    MapBuffers& m = h->map;
+    cudaFree(m.xyz); cudaFree(m.xyz_alt); cudaFree(m.keys); cudaFree(m.keys_sorted); cudaFree(m.vals); cudaFree(m.vals_sorted);
+    cudaFree(m.pts); cudaFree(m.table); cudaFree(m.counter); cudaFree(m.sort_tmp);
+    cudaFree(h->d_sweep); cudaFree(h->d_ctrl); cudaFreeHost(h->h_ctrl); cudaFree(h->d_partials);
+    cudaFree(h->d_reduced); cudaFreeHost(h->h_reduced); cudaFree(h->d_flush);
+    cudaFree(h->d_valid); cudaFree(h->d_nn_idx); cudaFree(h->d_nn_sqd); cudaFree(h->d_plane);
+    cudaFree(h->d_dist); cudaFree(h->d_gworld); cudaFree(h->d_rows);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+/* ---- Mapper ---------------------------------------------------------------------------------- */
+static lv_status rebuild(lv_context* h) {
+    EventPair ep;
+    const bool pr = prof_begin(h, 2, &ep);
+    int launches = 0;
+    LV_CUDA(map_rebuild(h->map, h->stream, &launches));
+    if (pr) prof_end(h, &ep);
+    h->prof.total_launches += launches;
+    return LV_OK;
+}
+
+lv_status lv_map_build(lv_handle h, const float* xyz, int64_t m) {
+    if (!h || (!xyz && m > 0)) return LV_ERR_ARG;
+    if (m <= 0) return LV_OK;                                    /* Mapper.cpp:23 */
+    if (m > h->map.cap) { set_error("map capacity exceeded"); return LV_ERR_CAPACITY; }
+    LV_CUDA(cudaSetDevice(h->prm.device));
+    LV_CUDA(cudaMemcpyAsync(h->map.xyz, xyz, sizeof(float) * 3 * m, cudaMemcpyHostToDevice, h->stream));
+    h->map.n = m;
+    return rebuild(h);
+}
+lv_status lv_map_build_device(lv_handle h, const float* d_xyz, int64_t m) {
+    if (!h || (!d_xyz && m > 0)) return LV_ERR_ARG;
+    if (m <= 0) return LV_OK;
+    if (m > h->map.cap) { set_error("map capacity exceeded"); return LV_ERR_CAPACITY; }
+    LV_CUDA(cudaSetDevice(h->prm.device));
+    LV_CUDA(cudaMemcpyAsync(h->map.xyz, d_xyz, sizeof(float) * 3 * m, cudaMemcpyDeviceToDevice, h->stream));
+    h->map.n = m;
+    return rebuild(h);
+}
+int64_t lv_map_size(lv_handle h) { return h ? h->map.n : 0; }
+int lv_map_exists(lv_handle h) { return (h && h->map.n > 0) ? 1 : 0; }
+int64_t lv_map_points(lv_handle h, float* out, int64_t cap) {
+    if (!h) return 0;
+    const int64_t n = h->map.n < cap ? h->map.n : cap;
+    if (n > 0 && out) {
+        cudaSetDevice(h->prm.device);
+        if (cudaMemcpyAsync(out, h->map.xyz, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) return -1;
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
+    }
+    return h->map.n;
+}
+
+lv_status lv_map_add(lv_handle h, const float* xyz, int64_t n, int downsample) {
+    if (!h || (!xyz && n > 0)) return LV_ERR_ARG;
+    if (n <= 0) return LV_OK;                                    /* Mapper.cpp:23 */
+    if (h->map.n == 0) return lv_map_build(h, xyz, n);           /* Mapper.cpp:26 */
+    LV_CUDA(cudaSetDevice(h->prm.device));
+    int launches = 0;
+    const lv_status st = (lv_status)lvh_map_add_points(h->map, xyz, n, downsample, h->prm.map_downsample_size, h->stream, &launches);
+    if (st != LV_OK) { set_error("lv_map_add failed (capacity or CUDA error)"); return st; }
+    h->prof.total_launches += launches;
+    return rebuild(h);
+}
+
+/* ---- state ----------------------------------------------------------------------------------- */
+static lv_status fetch_results(lv_context* h);
+static lv_status sync_mirror(lv_context* h) {   /* bring the host mirror up to date after lv_correct_device */
+    if (!h->pending_fetch) return LV_OK;
+    if (cudaSetDevice(h->prm.device) != cudaSuccess) return LV_ERR_CUDA;
+    fetch_results(h);
+    return LV_OK;
+}
+
+lv_status lv_set_state(lv_handle h, const double* x, const double* P) {
+    if (!h) return LV_ERR_ARG;
+    if (!(x && P)) sync_mirror(h);
+    if (x) memcpy(h->x, x, sizeof(h->x));
+    if (P) memcpy(h->P, P, sizeof(h->P));
+    h->state_dirty = true;
+    return LV_OK;
+}
+lv_status lv_get_state(lv_handle h, double* x, double* P) {
+    if (!h) return LV_ERR_ARG;
+    sync_mirror(h);
+    if (x) memcpy(x, h->x, sizeof(h->x));
+    if (P) memcpy(P, h->P, sizeof(h->P));
+    return LV_OK;
+}
+lv_status lv_init_state(lv_handle h, const float q_imu[4]) {
+    if (!h || !q_imu) return LV_ERR_ARG;
+    lvh_init_state(h->prm, q_imu, h->x, h->P);
+    h->state_dirty = true;
+    return LV_OK;
+}
+lv_status lv_predict(lv_handle h, const double acc[3], const double gyro[3], double dt) {
+    if (!h || !acc || !gyro) return LV_ERR_ARG;
+    sync_mirror(h);
+    lvh_predict(h->prm, acc, gyro, dt, h->x, h->P);
+    h->state_dirty = true;
+    return LV_OK;
+}
+double lv_last_time_updated(lv_handle h) { return h ? h->last_time_updated : -1; }
+
+static lv_status upload_state(lv_context* h, const double* x, const double* P) {
+    /* x, P are staged through the pinned mirror so the copy is truly asynchronous */
+    memcpy(h->h_ctrl->x, x, sizeof(double) * kStateLen);
+    LV_CUDA(cudaMemcpyAsync(h->d_ctrl->x, h->h_ctrl->x, sizeof(double) * kStateLen, cudaMemcpyHostToDevice, h->stream));
+    if (P) {
+        memcpy(h->h_ctrl->P, P, sizeof(double) * kN * kN);
+        LV_CUDA(cudaMemcpyAsync(h->d_ctrl->P, h->h_ctrl->P, sizeof(double) * kN * kN, cudaMemcpyHostToDevice, h->stream));
+    }
+    return LV_OK;
+}
+
+/* ---- the update ------------------------------------------------------------------------------ */
+static lv_status enqueue_update(lv_context* h, const float* d_xyz, int64_t n) {
+    if (h->state_dirty) {
+        lv_status s = upload_state(h, h->x, h->P);
+        if (s != LV_OK) return s;
+        h->state_dirty = false;
+    }
+    LV_CUDA(launch_ieskf_begin(h->d_ctrl, h->stream));
+    h->prof.total_launches += 1;
+    MeasureArgs a = make_measure_args(h, d_xyz, n);
+    const int grid = measure_grid((int)n);
+    for (int e = 0; e <= h->prm.MAX_NUM_ITERS; ++e) {            /* i = -1 .. max_iter-1, esekfom.hpp:1634 */
+        EventPair ep;
+        bool pr = prof_begin(h, 0, &ep);
+        LV_CUDA(launch_measure(a, grid, h->stream));
+        if (pr) prof_end(h, &ep);
+        pr = prof_begin(h, 1, &ep);
+        LV_CUDA(launch_ieskf_step(h->d_ctrl, h->iprm, h->d_partials, grid, h->stream));
+        if (pr) prof_end(h, &ep);
+        h->prof.total_launches += 2;
+    }
+    return LV_OK;
+}
+
+static lv_status fetch_results(lv_context* h) {
+    LV_CUDA(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, sizeof(UpdateCtrl), cudaMemcpyDeviceToHost, h->stream));
+    LV_CUDA(cudaStreamSynchronize(h->stream));
+    const UpdateCtrl* c = h->h_ctrl;
+    memcpy(h->x, c->x, sizeof(h->x));
+    if (c->status == LV_OK) memcpy(h->P, c->P, sizeof(h->P));
+    h->n_evals = c->n_evals;
+    memcpy(h->logs, c->logs, sizeof(h->logs));
+    h->last_status = c->status;
+    h->state_dirty = false;
+    h->pending_fetch = false;
+    return (lv_status)c->status;
+}
+
+lv_status lv_correct(lv_handle h, const float* xyz, int64_t n, double time, lv_iter_log* logs, int32_t* n_evals,
+                     double* x_out, double* P_out) {
+    if (!h || !xyz || n <= 0) return LV_ERR_ARG;
+    if (n_evals) *n_evals = 0;
+    if (h->map.n == 0) return LV_EMPTY_MAP;                       /* Localizator.cpp:24 */
+    if (n > h->prm.max_points) { set_error("sweep capacity exceeded"); return LV_ERR_CAPACITY; }
+    LV_CUDA(cudaSetDevice(h->prm.device));
+    LV_CUDA(cudaMemcpyAsync(h->d_sweep, xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
+    lv_status s = enqueue_update(h, h->d_sweep, n);
+    if (s != LV_OK) return s;
+    s = fetch_results(h);
+    h->last_time_updated = time;                                  /* Localizator.cpp:26 */
+    if (logs) memcpy(logs, h->logs, sizeof(lv_iter_log) * (size_t)h->n_evals);
+    if (n_evals) *n_evals = h->n_evals;
+    if (x_out) memcpy(x_out, h->x, sizeof(h->x));
+    if (P_out) memcpy(P_out, h->P, sizeof(h->P));
+    return s;
+}
+
+lv_status lv_correct_device(lv_handle h, const float* d_xyz, int64_t n, double time) {
+    if (!h || !d_xyz || n <= 0) return LV_ERR_ARG;
+    if (h->map.n == 0) return LV_EMPTY_MAP;
+    LV_CUDA(cudaSetDevice(h->prm.device));
+    lv_status s = enqueue_update(h, d_xyz, n);
+    h->last_time_updated = time;
+    h->pending_fetch = true;
+    return s;
+}
+
+lv_status lv_last_logs(lv_handle h, lv_iter_log* logs, int32_t* n_evals) {
+    if (!h) return LV_ERR_ARG;
+    LV_CUDA(cudaSetDevice(h->prm.device));
+    lv_status s = fetch_results(h);
+    if (logs) memcpy(logs, h->logs, sizeof(lv_iter_log) * (size_t)h->n_evals);
+    if (n_evals) *n_evals = h->n_evals;
+    return s;
+}
+
+/* ---- operator boundary ----------------------------------------------------------------------- */
+static lv_status run_measure_once(lv_context* h, const double* x, const float* xyz, int64_t n, bool want_rows,
+                                  bool want_debug) {
+    if (n > h->prm.max_points) { set_error("sweep capacity exceeded"); return LV_ERR_CAPACITY; }
+    LV_CUDA(cudaSetDevice(h->prm.device));
+    LV_CUDA(cudaMemcpyAsync(h->d_sweep, xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
+    lv_status s = upload_state(h, x, nullptr);
+    if (s != LV_OK) return s;
+    h->state_dirty = true;   /* d_ctrl->x no longer mirrors the filter */
+    LV_CUDA(launch_set_frame(h->d_ctrl, h->stream));
+    MeasureArgs a = make_measure_args(h, h->d_sweep, n);
+    const size_t mp = (size_t)h->prm.max_points;
+    if (want_rows) { LV_CUDA(ensure(&h->d_rows, 13 * mp)); LV_CUDA(ensure(&h->d_valid, mp)); a.rows = h->d_rows; a.valid = h->d_valid; }
+    if (want_debug) {
+        LV_CUDA(ensure(&h->d_valid, mp)); LV_CUDA(ensure(&h->d_nn_idx, 5 * mp)); LV_CUDA(ensure(&h->d_nn_sqd, 5 * mp));
+        LV_CUDA(ensure(&h->d_plane, 4 * mp)); LV_CUDA(ensure(&h->d_dist, mp)); LV_CUDA(ensure(&h->d_gworld, 3 * mp));
+        a.valid = h->d_valid; a.nn_idx = h->d_nn_idx; a.nn_sqd = h->d_nn_sqd; a.plane = h->d_plane; a.dist = h->d_dist;
+        a.g_world = h->d_gworld;
+    }
+    const int grid = measure_grid((int)n);
+    EventPair ep;
+    const bool pr = prof_begin(h, 0, &ep);
+    LV_CUDA(launch_measure(a, grid, h->stream));
+    if (pr) prof_end(h, &ep);
+    LV_CUDA(launch_reduce_partials(h->d_partials, grid, h->d_reduced, h->stream));
+    LV_CUDA(cudaMemcpyAsync(h->h_reduced, h->d_reduced, sizeof(double) * 157, cudaMemcpyDeviceToHost, h->stream));
+    h->prof.total_launches += 3;
+    return LV_OK;
+}
+
+lv_status lv_measure_reduced(lv_handle h, const double* x, const float* xyz, int64_t n, double* HTH, double* HTh,
+                             int64_t* nm) {
+    if (!h || !x || !xyz || n <= 0) return LV_ERR_ARG;
+    if (nm) *nm = 0;
+    if (h->map.n == 0) return LV_EMPTY_MAP;
+    lv_status s = run_measure_once(h, x, xyz, n, false, false);
+    if (s != LV_OK) return s;
+    LV_CUDA(cudaStreamSynchronize(h->stream));
+    if (HTH) memcpy(HTH, h->h_reduced, sizeof(double) * 144);
+    if (HTh) memcpy(HTh, h->h_reduced + 144, sizeof(double) * 12);
+    if (nm) *nm = (int64_t)h->h_reduced[156];
+    return LV_OK;
+}
+
+lv_status lv_measure(lv_handle h, const double* x, const float* xyz, int64_t n, double* h_x, double* h_vec, int64_t* nm) {
+    if (!h || !x || !xyz || n <= 0 || !nm) return LV_ERR_ARG;
+    *nm = 0;
+    if (h->map.n == 0) return LV_EMPTY_MAP;
+    lv_status s = run_measure_once(h, x, xyz, n, true, false);
+    if (s != LV_OK) return s;
+    std::vector<double> rows(13 * (size_t)n);
+    std::vector<uint8_t> valid((size_t)n);
+    LV_CUDA(cudaMemcpyAsync(rows.data(), h->d_rows, sizeof(double) * 13 * n, cudaMemcpyDeviceToHost, h->stream));
+    LV_CUDA(cudaMemcpyAsync(valid.data(), h->d_valid, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    LV_CUDA(cudaStreamSynchronize(h->stream));
+    /* compaction in input order = the single-thread order of Mapper::match (Mapper.cpp:46-53);
+     * layout: column-major Nm x 12 like Eigen::MatrixXd (Localizator.cpp:31) */
+    int64_t cnt = 0;
+    for (int64_t i = 0; i < n; ++i) cnt += valid[i] ? 1 : 0;
+    int64_t k = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (!valid[i]) continue;
+        if (h_x)
+            for (int c = 0; c < 12; ++c) h_x[(size_t)c * cnt + k] = rows[13 * (size_t)i + c];
+        if (h_vec) h_vec[k] = rows[13 * (size_t)i + 12];
+        ++k;
+    }
+    *nm = cnt;
+    return LV_OK;
+}
+
+lv_status lv_match_all(lv_handle h, const double* x, const float* xyz, int64_t n, uint8_t* valid, int32_t* nn_idx,
+                       float* nn_sqd, float* plane, float* dist, float* g_world) {
+    if (!h || !x || !xyz || n <= 0) return LV_ERR_ARG;
+    if (h->map.n == 0) return LV_EMPTY_MAP;
+    lv_status s = run_measure_once(h, x, xyz, n, false, true);
+    if (s != LV_OK) return s;
+    if (valid) LV_CUDA(cudaMemcpyAsync(valid, h->d_valid, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    if (nn_idx) LV_CUDA(cudaMemcpyAsync(nn_idx, h->d_nn_idx, sizeof(int32_t) * 5 * n, cudaMemcpyDeviceToHost, h->stream));
+    if (nn_sqd) LV_CUDA(cudaMemcpyAsync(nn_sqd, h->d_nn_sqd, sizeof(float) * 5 * n, cudaMemcpyDeviceToHost, h->stream));
+    if (plane) LV_CUDA(cudaMemcpyAsync(plane, h->d_plane, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost, h->stream));
+    if (dist) LV_CUDA(cudaMemcpyAsync(dist, h->d_dist, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+    if (g_world) LV_CUDA(cudaMemcpyAsync(g_world, h->d_gworld, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, h->stream));
+    LV_CUDA(cudaStreamSynchronize(h->stream));
+    return LV_OK;
+}
+
+/* ---- utilities ------------------------------------------------------------------------------- */
+void* lv_host_alloc(int64_t bytes) {
+    void* p = nullptr;
+    if (bytes <= 0 || cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+void lv_host_free(void* p) { if (p) cudaFreeHost(p); }
+void* lv_device_alloc(lv_handle h, int64_t bytes) {
+    if (!h || bytes <= 0) return nullptr;
+    void* p = nullptr;
+    cudaSetDevice(h->prm.device);
+    if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+void lv_device_free(lv_handle h, void* p) { if (h && p) { cudaSetDevice(h->prm.device); cudaFree(p); } }
+lv_status lv_memcpy_h2d(lv_handle h, void* dst, const void* src, int64_t bytes) {
+    if (!h || !dst || !src || bytes < 0) return LV_ERR_ARG;
+    LV_CUDA(cudaSetDevice(h->prm.device));
+    LV_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, h->stream));
+    LV_CUDA(cudaStreamSynchronize(h->stream));
+    return LV_OK;
+}
+lv_status lv_synchronize(lv_handle h) {
+    if (!h) return LV_ERR_ARG;
+    LV_CUDA(cudaSetDevice(h->prm.device));
+    LV_CUDA(cudaStreamSynchronize(h->stream));
+    return LV_OK;
+}
+lv_status lv_profile_enable(lv_handle h, int on) {
+    if (!h) return LV_ERR_ARG;
+    h->profile = on != 0;
+    return LV_OK;
+}
+lv_status lv_profile_get(lv_handle h, lv_profile* out, int reset) {
+    if (!h || !out) return LV_ERR_ARG;
+    LV_CUDA(cudaSetDevice(h->prm.device));
+    lv_status s = drain_events(h);
+    if (s != LV_OK) return s;
+    *out = h->prof;
+    if (reset) memset(&h->prof, 0, sizeof(h->prof));
+    return LV_OK;
+}
+lv_status lv_flush_l2(lv_handle h) {
+    if (!h) return LV_ERR_ARG;
+    LV_CUDA(cudaSetDevice(h->prm.device));
+    const size_t bytes = 256ull << 20;
+    if (!h->d_flush) LV_CUDA(cudaMalloc(&h->d_flush, bytes));
+    LV_CUDA(launch_l2_flush(h->d_flush, bytes, h->stream));
+    h->prof.total_launches += 1;
+    return LV_OK;
+}
+
+}  // extern "C"

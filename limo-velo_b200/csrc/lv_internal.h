@@ -1,0 +1,76 @@
+/*
+ * lv_internal.h — launcher declarations shared by the translation units of liblimovelo_b200.so.
+ */
+#ifndef LV_INTERNAL_H_
+#define LV_INTERNAL_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lv_ieskf.h"
+#include "lv_voxel_search.h"
+
+namespace lv {
+
+enum { kMeasureThreads = 128, kPartialStride = 96, kStepThreads = 512 };
+
+/* per-launch constants of the fused measure kernel */
+struct MeasureArgs {
+    const float* xyz;          /* n x 3 packed, LiDAR frame                               */
+    int32_t n;
+    int32_t n_tiles;           /* ceil(n / kMeasureThreads)                               */
+    VoxelMapView map;
+    const UpdateCtrl* ctrl;    /* frame + done flag                                       */
+    float max_d2;              /* smallest float >= MAX_DIST_PLANE^2 (search radius^2)    */
+    double gate_d2;            /* MAX_DIST_PLANE^2 in double (Plane.cpp:42)               */
+    int32_t max_ring;
+    float planes_threshold;
+    int32_t estimate_extrinsics;
+    double* partials;          /* [grid][kPartialStride]: 78 + 12 sums, count             */
+    /* optional per-point outputs (NULL on the hot path) */
+    uint8_t* valid;
+    int32_t* nn_idx;
+    float* nn_sqd;
+    float* plane;
+    float* dist;
+    float* g_world;
+    double* rows;              /* n x 13 (row[12], h)                                     */
+};
+
+/* device map storage + scratch for the per-sweep rebuild */
+struct MapBuffers {
+    float* xyz;                /* map points, insertion order (flatten order), cap x 3     */
+    float* xyz_alt;            /* second buffer: lv_map_add compacts into it, then swaps    */
+    int64_t n, cap;
+    uint64_t* keys;            /* cap */
+    uint64_t* keys_sorted;     /* cap */
+    uint32_t* vals;
+    uint32_t* vals_sorted;
+    float4* pts;               /* cap, sorted by voxel key                                 */
+    uint4* table;              /* table_cap slots                                          */
+    uint32_t table_cap;        /* allocated slots (power of two)                           */
+    uint32_t table_mask;       /* slots in use - 1                                         */
+    uint32_t* counter;         /* device scalar                                            */
+    void* sort_tmp;
+    size_t sort_tmp_bytes;
+    float cell, inv_cell;
+};
+
+size_t map_sort_tmp_bytes(int64_t cap);
+/* K0: rebuild the hashed-voxel structure from b.xyz[0..n).  Returns launches issued; synchronises
+ * the stream once (to size the hash table).                                                    */
+cudaError_t map_rebuild(MapBuffers& b, cudaStream_t st, int* launches);
+VoxelMapView map_view(const MapBuffers& b);
+
+int measure_grid(int n);
+cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st);
+cudaError_t launch_ieskf_begin(UpdateCtrl* c, cudaStream_t st);
+cudaError_t launch_ieskf_step(UpdateCtrl* c, const IeskfParams& prm, const double* partials, int n_partials,
+                              cudaStream_t st);
+/* stand-alone reduction of the partials (operator-boundary calls): out[0:144) HTH, [144:156) HTh, [156] Nm */
+cudaError_t launch_reduce_partials(const double* partials, int n_partials, double* out, cudaStream_t st);
+cudaError_t launch_set_frame(UpdateCtrl* c, cudaStream_t st);   /* frame from c->x, done = 0 */
+cudaError_t launch_l2_flush(void* buf, size_t bytes, cudaStream_t st);
+
+}  // namespace lv
+#endif
