@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py — LIMO-Velo localization hot path on B200: matched-points/sec per IESKF iteration.
+
+One "step" = one Localizator::correct (all <= MAX_NUM_ITERS+1 h-evaluations of the iterated update:
+world transform -> exact 5-NN -> plane fit -> residual/Jacobian -> HtH/Hth -> 23-DoF IESKF step)
+on one synthetic 64k-point Velodyne sweep against a 1M-point map (BASELINE.json configs[1],
+config/xaloc.yaml).  Prints ONE JSON line (see the task contract); `--impl reference` times the CPU
+oracle (reference ikd-Tree compiled verbatim into oracle/_ref + restated plane/Jacobian/IESKF).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as G  # noqa: E402
+
+METRIC = "matched-points/sec per IESKF iteration (64k-pt sweep, 1M-pt map)"
+UNIT = "point-evaluations/s"
+SEED = 20260924
+MAP_POINTS = 1_000_000
+RINGS, AZIMUTHS = 64, 1024           # Velodyne-64 pattern: 65 536 beams
+N_SWEEPS = 8                          # distinct sweeps along the road, replayed round-robin
+ALGO_BYTES_PER_POINT = 72             # 12 B query + 5 x 12 B neighbours
+
+
+def workload_config(n_gpus):
+    return {"workload": "cfg1: xaloc.yaml, %d-pt Velodyne-64 sweep vs %d-pt map, MAX_NUM_ITERS=3 (<=4 evaluations)"
+                        % (RINGS * AZIMUTHS, MAP_POINTS),
+            "sweep_points": RINGS * AZIMUTHS, "map_points": MAP_POINTS, "yaml": "xaloc.yaml",
+            "sequences": n_gpus, "parallelism": "one independent sequence per GPU (no data-path collective)",
+            "l2": "flushed (256 MiB write) between timed steps; step time = CUDA events around each update"}
+
+
+def make_scene(lv, rank, n_sweeps=N_SWEEPS, prm=None):
+    """Seeded world + sweeps + predicted states for one sequence (seed base + 1 + rank: SURVEY 8d cfg1/cfg4)."""
+    O = G.load_oracle()
+    world = lv.SynthWorld(SEED + 1 + 10 * rank, MAP_POINTS)
+    mp = world.map()
+    rng = np.random.default_rng(SEED + 1000 + rank)
+    sweeps, x_props, truths = [], [], []
+    for i in range(n_sweeps):
+        truth = world.pose(15.0 + 1.5 * i, prm)            # 15 m/s at 10 Hz
+        sweeps.append(world.sweep(truth, rings=RINGS, azimuths=AZIMUTHS, min_dist=4.0, range_sigma=0.02, seed=100 + i))
+        d = np.zeros(23)
+        d[0:3] = rng.uniform(-0.05, 0.05, 3)
+        d[3:6] = rng.uniform(-0.5, 0.5, 3) * np.pi / 180.0
+        x_props.append(O.boxplus(truth, d))
+        truths.append(truth)
+    return world, mp, sweeps, x_props, truths
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [s.strip() for s in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def oracle_params(O, prm):
+    return O.make_params(max_num_iters=prm.MAX_NUM_ITERS, estimate_extrinsics=prm.estimate_extrinsics,
+                         max_dist_plane=prm.MAX_DIST_PLANE, planes_threshold=prm.PLANES_THRESHOLD,
+                         lidar_noise=prm.LiDAR_noise, degeneracy_threshold=prm.degeneracy_threshold,
+                         limits=list(prm.LIMITS))
+
+
+def cpu_leg(lv, prm, mp, sweeps, x_props, P0, budget_s, threads, max_updates=None):
+    """Time the CPU oracle (Localizator::correct restated; kNN = the reference's own ikd-Tree when
+    oracle/_ref is present) on whole updates of the same workload until `budget_s` is used."""
+    O = G.load_oracle()
+    kind = "reference" if O.ref_available() else "port"
+    om = O.Map(O.KNN_REF_IKDTREE if kind == "reference" else O.KNN_KDTREE)
+    om.build(mp)
+    om.knn(mp[0])                       # forces the lazy tree build of the port backend
+    O.set_threads(threads)
+    oprm = oracle_params(O, prm)
+    pts, secs, n_upd = 0, 0.0, 0
+    t_start = time.perf_counter()
+    i = 0
+    while True:
+        t0 = time.perf_counter()
+        st, x, P, logs = om.update_iterated(x_props[i % len(sweeps)], P0, oprm, sweeps[i % len(sweeps)])
+        dt = time.perf_counter() - t0
+        pts += sweeps[i % len(sweeps)].shape[0] * len(logs)
+        secs += dt
+        n_upd += 1
+        i += 1
+        if (max_updates and n_upd >= max_updates) or (not max_updates and time.perf_counter() - t_start > budget_s):
+            break
+    what = ("%d full updates (%d-pt sweep, %d-pt map, %d point-evaluations) in %.1f s; kNN = %s" %
+            (n_upd, sweeps[0].shape[0], mp.shape[0], pts, secs,
+             "reference ikd_Tree.cpp compiled verbatim (oracle/_ref)" if kind == "reference" else "oracle kd-tree port"))
+    return {"value": pts / secs, "unit": UNIT, "cores": threads, "kind": kind, "sample": what}, pts, secs, n_upd
+
+
+def run_reference(args, rank, world_size):
+    if rank != 0:
+        return
+    lv = G.load_package()
+    prm = lv.params_from_yaml(os.path.join(lv.CONFIG_DIR, "xaloc.yaml"))
+    O = G.load_oracle()
+    _, mp, sweeps, x_props, _ = make_scene(lv, 0, n_sweeps=4, prm=prm)
+    x0, P0 = O.init_state(initial_gravity=prm.initial_gravity[:], I_Rotation_L=prm.I_Rotation_L[:],
+                          I_Translation_L=prm.I_Translation_L[:])
+    ncores = os.cpu_count() or 1
+    threads = 3 if ncores > 4 else (2 if ncores == 4 else 1)      # MP_PROC_NUM rule, CMakeLists.txt:19-36
+    cpu_leg(lv, prm, mp, sweeps, x_props, P0, 0, threads, max_updates=max(1, args.warmup if args.warmup < 2 else 1))
+    base, pts, secs, n_upd = cpu_leg(lv, prm, mp, sweeps, x_props, P0, 0, threads, max_updates=args.steps)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / n_upd, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 geometry / f64 Jacobian+filter", "data": "synthetic",
+            "config": workload_config(args.gpus), "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "host_cpu_count": ncores}
+    print(json.dumps(line), flush=True)
+
+
+def run_native(args, rank, local_rank, world_size):
+    import torch
+    import torch.distributed as dist
+    lv = G.load_package()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.Stream()            # a real (non-default) stream: the library launches on it
+    torch.cuda.set_stream(stream)
+    prm = lv.params_from_yaml(os.path.join(lv.CONFIG_DIR, "xaloc.yaml"), device=local_rank,
+                              max_map_points=MAP_POINTS + 4 * RINGS * AZIMUTHS, max_points=RINGS * AZIMUTHS,
+                              stream=stream.cuda_stream)
+    world, mp, sweeps, x_props, truths = make_scene(lv, rank, prm=prm)
+    n = sweeps[0].shape[0]
+    loc = lv.Localizer(prm)
+    loc.map_build(mp)
+    loc.init_state()
+    _, P0 = loc.get_state()
+    d_sweeps = [loc.upload(s) for s in sweeps]                      # inputs resident in HBM for `value`
+    pinned = [lv.PinnedBuffer((n, 3)) for _ in sweeps]              # pinned host copies for `e2e`
+    for pb, s in zip(pinned, sweeps):
+        pb.array[:] = s
+
+    def step_device(i):
+        loc.set_state(x_props[i % len(sweeps)], P0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        loc.correct_device(d_sweeps[i % len(sweeps)], n)
+        e1.record(stream)
+        st, logs = loc.last_logs()                                  # syncs; outside the timed events
+        loc.flush_l2()
+        return e0, e1, logs
+
+    for i in range(args.warmup):
+        step_device(i)
+    torch.cuda.synchronize()
+    if world_size > 1:
+        dist.barrier()
+    loc.profile_enable(True)
+    loc.profile(reset=True)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    evs, evals, matched = [], 0, 0
+    for i in range(args.steps):
+        e0, e1, logs = step_device(args.warmup + i)
+        evs.append((e0, e1))
+        evals += len(logs)
+        matched += sum(l["n_matches"] for l in logs)
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    if world_size > 1:
+        dist.barrier()
+    clock_info = clocks.stop()
+    prof = loc.profile(reset=True)
+    loc.profile_enable(False)
+    step_ms = sum(a.elapsed_time(b) for a, b in evs)
+    pts = n * evals
+
+    # ---- e2e: the public host-buffer call, pinned H2D + kernels + D2H of the result, wall clock ----
+    for i in range(min(3, args.warmup)):
+        loc.set_state(x_props[i % len(sweeps)], P0)
+        loc.correct(None, raw_ptr=pinned[i % len(sweeps)].ptr, n=n)
+    e2e_s, e2e_pts = 0.0, 0
+    for i in range(args.steps):
+        j = (args.warmup + i) % len(sweeps)
+        loc.flush_l2()
+        loc.synchronize()
+        loc.set_state(x_props[j], P0)
+        t0 = time.perf_counter()
+        st, x, P, logs = loc.correct(None, raw_ptr=pinned[j].ptr, n=n)
+        e2e_s += time.perf_counter() - t0
+        e2e_pts += n * len(logs)
+    pose_err = float(np.abs(G.load_oracle().boxminus(x, truths[j]))[:3].max())
+
+    # ---- per-sweep map update (Mapper::add + rebuild), reported beside the headline ----
+    t_add = []
+    for i in range(2):
+        gpts = world_points(sweeps[i], truths[i])
+        loc.synchronize()
+        t0 = time.perf_counter()
+        loc.map_add(gpts, downsample=True)
+        loc.synchronize()
+        t_add.append(time.perf_counter() - t0)
+
+    # ---- max over ranks / totals ----
+    tot = torch.tensor([step_ms, float(pts), float(matched), e2e_s, float(e2e_pts), float(prof["total_launches"])],
+                       dtype=torch.float64, device="cuda")
+    if world_size > 1:
+        mx = tot.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tot.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        step_ms_max, e2e_s_max = float(mx[0]), float(mx[3])
+        pts_all, matched_all, e2e_pts_all, launches_all = float(sm[1]), float(sm[2]), float(sm[4]), float(sm[5])
+    else:
+        step_ms_max, e2e_s_max = step_ms, e2e_s
+        pts_all, matched_all, e2e_pts_all, launches_all = float(pts), float(matched), float(e2e_pts), float(prof["total_launches"])
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        m_launches = max(1, prof["measure_launches"])
+        m_ms = prof["measure_ms"] / m_launches
+        achieved = ALGO_BYTES_PER_POINT * n / (m_ms * 1e-3) / 1e9 if m_ms > 0 else 0.0
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "measure_kernel_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        cpu = None
+        if not args.no_cpu:
+            O = G.load_oracle()
+            cpu, _, _, _ = cpu_leg(lv, prm, mp, sweeps, x_props, P0, args.cpu_seconds, 1)
+        sz_ctrl = 8 * (26 + 529) * 2 + 32 + 8 * (8 + 8 + 8 * (144 + 12 + 23 + 26)) + 400
+        line = {
+            "metric": METRIC, "value": pts_all / (step_ms_max * 1e-3), "unit": UNIT, "n_gpus": world_size,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 geometry / f64 Jacobian+filter", "data": "synthetic", "config": workload_config(world_size),
+            "evaluations_per_step": evals / args.steps, "accept_rate": matched_all / max(1.0, pts_all),
+            "matched_points_per_s": matched_all / (step_ms_max * 1e-3),
+            "wall_ms_total_incl_flush_and_readback": 1e3 * t_wall,
+            "e2e": {"value": e2e_pts_all / e2e_s_max, "unit": UNIT, "h2d_bytes_per_step": n * 12 + 8 * (26 + 529),
+                    "d2h_bytes_per_step": sz_ctrl, "ms_per_step": 1e3 * e2e_s_max / args.steps,
+                    "how": "lv_correct() on a pinned host sweep, wall clock around the blocking call"},
+            "gpu_launches": int(round(launches_all)) - args.steps * world_size,   # minus the L2-flush kernels
+            "kernel_ms": {"measure_avg": m_ms, "measure_launches": prof["measure_launches"],
+                          "idle_measure_launches": prof.get("idle_launches", 0),
+                          "solve_avg": prof["solve_ms"] / max(1, prof["solve_launches"]),
+                          "solve_launches": prof["solve_launches"]},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                         "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "lv_measure_kernel", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_POINT * n},
+            "cpu_baseline": cpu,
+            "map_update": {"lv_map_add_ms": 1e3 * min(t_add), "points_added": n, "map_points": loc.map_size()},
+            "final_position_error_m": pose_err,
+            "clocks": clock_info,
+        }
+        print(json.dumps(line), flush=True)
+    for pb in pinned:
+        pb.free()
+    loc.close()
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+def world_points(sweep, x):
+    """LiDAR-frame sweep -> world frame with the true state (what main.cpp:101 hands to map.add)."""
+    O = G.load_oracle()
+    R = O.quat_to_rot(x[3:7])
+    RL = O.quat_to_rot(x[7:11])
+    p_imu = sweep.astype(np.float64) @ RL.T + x[11:14]
+    return (p_imu @ R.T + x[0:3]).astype(np.float32)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world_size)
+    else:
+        run_native(args, rank, local_rank, world_size)
+
+
+if __name__ == "__main__":
+    main()

@@ -101,6 +101,8 @@ typedef struct lv_profile {
     double build_ms;          /* sum of device time of map (re)builds                      */
     int64_t measure_launches, solve_launches, build_launches;
     int64_t total_launches;   /* every kernel launched by this handle since the last reset */
+    double idle_ms;           /* launches that found the update already finished (early exit) */
+    int64_t idle_launches;
 } lv_profile;
 
 /* ------------------------------------------------------------------------------------------ */

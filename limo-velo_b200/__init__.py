@@ -48,7 +48,7 @@ class IterLog(C.Structure):
 class Profile(C.Structure):
     _fields_ = [("measure_ms", C.c_double), ("solve_ms", C.c_double), ("build_ms", C.c_double),
                 ("measure_launches", C.c_int64), ("solve_launches", C.c_int64), ("build_launches", C.c_int64),
-                ("total_launches", C.c_int64)]
+                ("total_launches", C.c_int64), ("idle_ms", C.c_double), ("idle_launches", C.c_int64)]
 
 
 def build(verbose=False):

@@ -8,6 +8,7 @@
  */
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -38,7 +39,8 @@ static void set_error(const std::string& s) { g_last_error = s; }
         }                                                                                        \
     } while (0)
 
-struct EventPair { cudaEvent_t a, b; int kind; };   /* kind 0 measure, 1 solve, 2 build */
+struct EventPair { cudaEvent_t a, b; int kind; int upd; int slot; };   /* kind 0 measure, 1 solve, 2 build */
+enum { kNevalsRing = 4096 };
 
 struct lv_context {
     lv_params prm;
@@ -49,6 +51,9 @@ struct lv_context {
     UpdateCtrl* d_ctrl = nullptr;
     UpdateCtrl* h_ctrl = nullptr;      /* pinned mirror for the D2H of results */
     double* d_partials = nullptr;
+    int4* d_nn_a = nullptr;            /* max_points: K1 -> K2 hand-over */
+    int2* d_nn_b = nullptr;
+    uint32_t* d_hard_list = nullptr;   /* max_points + 1: work list of K1b and its length */
     double* d_reduced = nullptr;       /* 157 doubles */
     double* h_reduced = nullptr;       /* pinned */
     void* d_flush = nullptr;
@@ -69,6 +74,8 @@ struct lv_context {
     std::vector<EventPair> pending;
     std::vector<EventPair> pool;
     lv_profile prof;
+    int32_t* h_nevals = nullptr;       /* pinned ring: n_evals of profiled updates */
+    uint32_t update_seq = 0;
     IeskfParams iprm;
 };
 
@@ -78,7 +85,10 @@ static lv_status drain_events(lv_context* h) {
     for (auto& e : h->pending) {
         float ms = 0;
         LV_CUDA(cudaEventElapsedTime(&ms, e.a, e.b));
-        if (e.kind == 0) { h->prof.measure_ms += ms; h->prof.measure_launches++; }
+        /* launches enqueued after the update had already finished return immediately: keep them apart */
+        const bool idle = e.upd >= 0 && e.slot >= h->h_nevals[e.upd % kNevalsRing];
+        if (idle) { h->prof.idle_ms += ms; h->prof.idle_launches++; }
+        else if (e.kind == 0) { h->prof.measure_ms += ms; h->prof.measure_launches++; }
         else if (e.kind == 1) { h->prof.solve_ms += ms; h->prof.solve_launches++; }
         else { h->prof.build_ms += ms; h->prof.build_launches++; }
         h->pool.push_back(e);
@@ -88,7 +98,7 @@ static lv_status drain_events(lv_context* h) {
 }
 static bool prof_begin(lv_context* h, int kind, EventPair* ep) {
     if (!h->profile) return false;
-    if (h->pending.size() > 8192) drain_events(h);
+    if (h->pending.size() > 2048) drain_events(h);
     if (h->pool.empty()) {
         EventPair e;
         if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return false;
@@ -97,6 +107,8 @@ static bool prof_begin(lv_context* h, int kind, EventPair* ep) {
     *ep = h->pool.back();
     h->pool.pop_back();
     ep->kind = kind;
+    ep->upd = -1;
+    ep->slot = 0;
     cudaEventRecord(ep->a, h->stream);
     return true;
 }
@@ -126,11 +138,14 @@ static MeasureArgs make_measure_args(lv_context* h, const float* d_xyz, int64_t 
     float f = (float)a.gate_d2;
     if ((double)f < a.gate_d2) f = nextafterf(f, INFINITY);
     a.max_d2 = f;
-    a.max_ring = (int32_t)ceil(md / (double)h->map.cell);
-    if (a.max_ring < 1) a.max_ring = 1;
+    a.max_ring = 1;
     a.planes_threshold = h->prm.PLANES_THRESHOLD;
     a.estimate_extrinsics = h->prm.estimate_extrinsics;
     a.partials = h->d_partials;
+    a.nn_a = h->d_nn_a;
+    a.nn_b = h->d_nn_b;
+    a.hard_list = h->d_hard_list;
+    a.hard_count = h->d_hard_list + h->prm.max_points;
     return a;
 }
 
@@ -170,9 +185,6 @@ lv_status lv_create(const lv_params* p, lv_handle* out) {
     m.cap = p->max_map_points;
     m.cell = p->voxel_size;
     m.inv_cell = 1.0f / p->voxel_size;
-    uint32_t tcap = 1024;
-    while ((uint64_t)tcap < 2ull * (uint64_t)m.cap && tcap < 0x80000000u) tcap <<= 1;
-    m.table_cap = tcap;
     m.sort_tmp_bytes = map_sort_tmp_bytes(m.cap);
     { const size_t t2 = lvh_map_add_tmp_bytes(m.cap); if (t2 > m.sort_tmp_bytes) m.sort_tmp_bytes = t2; }
     LV_CUDA(cudaMalloc(&m.xyz, sizeof(float) * 3 * m.cap));
@@ -182,16 +194,26 @@ lv_status lv_create(const lv_params* p, lv_handle* out) {
     LV_CUDA(cudaMalloc(&m.vals, sizeof(uint32_t) * m.cap));
     LV_CUDA(cudaMalloc(&m.vals_sorted, sizeof(uint32_t) * m.cap));
     LV_CUDA(cudaMalloc(&m.pts, sizeof(float4) * m.cap));
-    LV_CUDA(cudaMalloc(&m.table, sizeof(uint4) * (size_t)m.table_cap));
-    LV_CUDA(cudaMalloc(&m.counter, sizeof(uint32_t) * 4));
+    /* pyramid: edge doubles per level until it covers the search radius MAX_DIST_PLANE */
+    m.n_levels = 1;
+    while (m.n_levels < kMaxLevels && (double)m.cell * (double)(1 << (m.n_levels - 1)) < p->MAX_DIST_PLANE) m.n_levels++;
+    if ((double)m.cell * (double)(1 << (m.n_levels - 1)) < p->MAX_DIST_PLANE) {
+        set_error("voxel_size too small: voxel_size * 8 must reach MAX_DIST_PLANE");
+        return LV_ERR_ARG;
+    }
+    LV_CUDA(cudaMalloc(&m.counter, sizeof(uint32_t) * 8));
     LV_CUDA(cudaMalloc(&m.sort_tmp, m.sort_tmp_bytes));
     LV_CUDA(cudaMalloc(&h->d_sweep, sizeof(float) * 3 * p->max_points));
+    LV_CUDA(cudaMalloc(&h->d_nn_a, sizeof(int4) * p->max_points));
+    LV_CUDA(cudaMalloc(&h->d_nn_b, sizeof(int2) * p->max_points));
+    LV_CUDA(cudaMalloc(&h->d_hard_list, sizeof(uint32_t) * (p->max_points + 1)));
     LV_CUDA(cudaMalloc(&h->d_ctrl, sizeof(UpdateCtrl)));
     LV_CUDA(cudaMemset(h->d_ctrl, 0, sizeof(UpdateCtrl)));
     LV_CUDA(cudaMallocHost(&h->h_ctrl, sizeof(UpdateCtrl)));
     LV_CUDA(cudaMalloc(&h->d_partials, sizeof(double) * kPartialStride * (148 * 4 + 8)));
     LV_CUDA(cudaMalloc(&h->d_reduced, sizeof(double) * 160));
     LV_CUDA(cudaMallocHost(&h->h_reduced, sizeof(double) * 160));
+    LV_CUDA(cudaMallocHost(&h->h_nevals, sizeof(int32_t) * kNevalsRing));
     /* default filter state: identity pose, P = I (esekf constructor); callers normally follow
      * with lv_init_state or lv_set_state */
     for (int i = 0; i < LV_STATE_LEN; ++i) h->x[i] = 0;
@@ -209,9 +231,12 @@ void lv_destroy(lv_handle h) {
     for (auto& e : h->pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     MapBuffers& m = h->map;
     cudaFree(m.xyz); cudaFree(m.xyz_alt); cudaFree(m.keys); cudaFree(m.keys_sorted); cudaFree(m.vals); cudaFree(m.vals_sorted);
-    cudaFree(m.pts); cudaFree(m.table); cudaFree(m.counter); cudaFree(m.sort_tmp);
-    cudaFree(h->d_sweep); cudaFree(h->d_ctrl); cudaFreeHost(h->h_ctrl); cudaFree(h->d_partials);
-    cudaFree(h->d_reduced); cudaFreeHost(h->h_reduced); cudaFree(h->d_flush);
+    cudaFree(m.pts);
+    for (int l = 0; l < kMaxLevels; ++l) cudaFree(m.level[l].table);
+    cudaFree(m.halo); cudaFree(m.bsize); cudaFree(m.bstart);
+    cudaFree(m.counter); cudaFree(m.sort_tmp);
+    cudaFree(h->d_sweep); cudaFree(h->d_nn_a); cudaFree(h->d_nn_b); cudaFree(h->d_hard_list); cudaFree(h->d_ctrl); cudaFreeHost(h->h_ctrl); cudaFree(h->d_partials);
+    cudaFree(h->d_reduced); cudaFreeHost(h->h_reduced); cudaFreeHost(h->h_nevals); cudaFree(h->d_flush);
     cudaFree(h->d_valid); cudaFree(h->d_nn_idx); cudaFree(h->d_nn_sqd); cudaFree(h->d_plane);
     cudaFree(h->d_dist); cudaFree(h->d_gworld); cudaFree(h->d_rows);
     if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -336,12 +361,19 @@ static lv_status enqueue_update(lv_context* h, const float* d_xyz, int64_t n) {
     for (int e = 0; e <= h->prm.MAX_NUM_ITERS; ++e) {            /* i = -1 .. max_iter-1, esekfom.hpp:1634 */
         EventPair ep;
         bool pr = prof_begin(h, 0, &ep);
+        ep.upd = (int)(h->update_seq % kNevalsRing); ep.slot = e;
         LV_CUDA(launch_measure(a, grid, h->stream));
         if (pr) prof_end(h, &ep);
         pr = prof_begin(h, 1, &ep);
+        ep.upd = (int)(h->update_seq % kNevalsRing); ep.slot = e;
         LV_CUDA(launch_ieskf_step(h->d_ctrl, h->iprm, h->d_partials, grid, h->stream));
         if (pr) prof_end(h, &ep);
-        h->prof.total_launches += 2;
+        h->prof.total_launches += 4;
+    }
+    if (h->profile) {
+        LV_CUDA(cudaMemcpyAsync(&h->h_nevals[h->update_seq % kNevalsRing], &h->d_ctrl->n_evals, sizeof(int32_t),
+                                cudaMemcpyDeviceToHost, h->stream));
+        h->update_seq++;
     }
     return LV_OK;
 }
@@ -424,7 +456,7 @@ static lv_status run_measure_once(lv_context* h, const double* x, const float* x
     if (pr) prof_end(h, &ep);
     LV_CUDA(launch_reduce_partials(h->d_partials, grid, h->d_reduced, h->stream));
     LV_CUDA(cudaMemcpyAsync(h->h_reduced, h->d_reduced, sizeof(double) * 157, cudaMemcpyDeviceToHost, h->stream));
-    h->prof.total_launches += 3;
+    h->prof.total_launches += 5;
     return LV_OK;
 }
 

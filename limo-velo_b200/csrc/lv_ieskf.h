@@ -60,8 +60,7 @@ struct UpdateCtrl {
 struct IeskfWork {
     double x[kStateLen], xp[kStateLen];
     double P[kN * kN];        /* P_ after the J blocks (esekfom.hpp:1655-1697)           */
-    double M1[kN * kAug];     /* Gauss-Jordan scratch: [A | I]                            */
-    double M2[kN * kAug];
+    double M1[12 * 25];       /* Gauss-Jordan scratch: [I + Q S11 | Q | HTh]              */
     double Kx[kN * 12];
     double Kh[kN];
     double HTH[144], HTh[12];
@@ -79,42 +78,57 @@ struct ExecSerial {
     int tid, nthreads;
     LV_HD ExecSerial() : tid(0), nthreads(1) {}
     LV_HD void sync() {}
+    /* partial pivoting: row p >= k with the largest |M[p][k]| (first one on ties) */
+    LV_HD void pivot(const double* M, int w, int k, int n, int32_t* s_piv, double* s_pivval) {
+        int p = k;
+        double best = fabs(M[k * w + k]);
+        for (int i = k + 1; i < n; ++i) {
+            const double v = fabs(M[i * w + k]);
+            if (v > best) { best = v; p = i; }
+        }
+        *s_piv = p;
+        *s_pivval = M[p * w + k];
+    }
 };
 #if defined(__CUDACC__)
 struct ExecBlock {
     int tid, nthreads;
     __device__ __forceinline__ ExecBlock() : tid(threadIdx.x), nthreads(blockDim.x) {}
     __device__ __forceinline__ void sync() { __syncthreads(); }
+    /* same rule, one warp: lane i holds row k+i (n - k <= 32), shuffle arg-max, lowest row on ties */
+    __device__ __forceinline__ void pivot(const double* M, int w, int k, int n, int32_t* s_piv, double* s_pivval) {
+        if (tid < 32) {
+            const int row = k + tid;
+            double v = row < n ? fabs(M[row * w + k]) : -1.0;
+            int r = row < n ? row : 0x7fffffff;
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, v, s);
+                const int orow = __shfl_xor_sync(0xffffffffu, r, s);
+                if (ov > v || (ov == v && orow < r)) { v = ov; r = orow; }
+            }
+            if (tid == 0) { *s_piv = r; *s_pivval = M[r * w + k]; }
+        }
+    }
 };
 #endif
 
 #define LV_PAR(i, n) for (int i = ex.tid; i < (n); i += ex.nthreads)
 
-/* In-place inverse by Gauss-Jordan elimination with partial pivoting on M = [A | I] (n x 2n,
- * row-major).  The inverse ends up in the right half.  Eigen's fixed-size inverse() for n > 4
- * is PartialPivLU (esekfom.hpp:1722,1726); same pivoting rule, different elimination order.  */
+/* Gauss-Jordan elimination with partial pivoting on M = [A | B] (n rows, w >= n columns, row-major):
+ * on return the columns n..w-1 hold A^-1 B (the left block is not cleaned up).                   */
 template <class Ex>
-LV_HD_NOINLINE void gj_inverse(Ex& ex, double* M, int n, int32_t* s_piv, double* s_pivval) {
-    const int w = 2 * n;
+LV_HD_NOINLINE void gj_solve(Ex& ex, double* M, int n, int w, int32_t* s_piv, double* s_pivval) {
     for (int k = 0; k < n; ++k) {
-        if (ex.tid == 0) {
-            int p = k;
-            double best = fabs(M[k * w + k]);
-            for (int i = k + 1; i < n; ++i) {
-                const double v = fabs(M[i * w + k]);
-                if (v > best) { best = v; p = i; }
-            }
-            *s_piv = p;
-            *s_pivval = M[p * w + k];
-        }
+        ex.pivot(M, w, k, n, s_piv, s_pivval);
         ex.sync();
         const int p = *s_piv;
-        const double pv = *s_pivval;
+        const double ipv = 1.0 / *s_pivval;
         LV_PAR(jj, w - k) {
             const int j = k + jj;
             const double a = M[k * w + j], b = M[p * w + j];
             if (p != k) M[p * w + j] = a;
-            M[k * w + j] = b / pv;
+            M[k * w + j] = b * ipv;
         }
         ex.sync();
         const int ncols = w - k - 1;
@@ -328,38 +342,36 @@ LV_HD_NOINLINE void ieskf_step(Ex& ex, const IeskfParams& prm, UpdateCtrl* c, Ie
         ex.sync();
     }
 
-    /* P_temp = (P/R)^-1 ; += HTH ; P_inv = P_temp^-1   (esekfom.hpp:1722-1726) */
-    LV_PAR(it, n * kAug) {
-        const int i = it / kAug, j = it - i * kAug;
-        w->M1[it] = j < n ? w->P[i * n + j] / prm.R : (j - n == i ? 1.0 : 0.0);
-    }
-    ex.sync();
-    gj_inverse(ex, w->M1, n, &w->piv, &w->pivval);
-    LV_PAR(it, n * kAug) {
-        const int i = it / kAug, j = it - i * kAug;
+    /* Gain (esekfom.hpp:1722-1729).  The reference forms P_inv = ((P/R)^-1 + E^T Q E)^-1 with two 23x23
+     * inverses (Q = HTH, E = [I12 0]) and uses only P_inv[:, :12].  With S = P/R the matrix-inversion
+     * lemma gives  P_inv[:, :12] = S[:, :12] (I12 + Q S11)^-1  exactly, also for singular Q
+     * (estimate_extrinsics = false).  So one 12x12 system with 13 right-hand sides replaces both
+     * inverses:  Y = (I + Q S11)^-1 [Q | HTh],  K_x[:, :12] = S[:, :12] Y[:, :12],  K_h = S[:, :12] Y[:, 12].
+     * Against exact arithmetic this is at least as accurate as the reference's formulation
+     * ("gain formulation").                                                              */
+    const double invR = 1.0 / prm.R;
+    LV_PAR(it, 12 * 25) {
+        const int i = it / 25, j = it - i * 25;
         double v;
-        if (j < n) {
-            v = w->M1[i * kAug + n + j];
-            if (i < 12 && j < 12) v += w->HTH[i * 12 + j];
+        if (j < 12) {
+            double s = 0;
+            for (int k = 0; k < 12; ++k) s += w->HTH[i * 12 + k] * w->P[k * n + j];
+            v = s * invR + (i == j ? 1.0 : 0.0);
+        } else if (j < 24) {
+            v = w->HTH[i * 12 + (j - 12)];
         } else {
-            v = (j - n == i) ? 1.0 : 0.0;
+            v = w->HTh[i];
         }
-        w->M2[it] = v;
+        w->M1[it] = v;
     }
     ex.sync();
-    gj_inverse(ex, w->M2, n, &w->piv, &w->pivval);
-    /* K_h = P_inv[:, :12] HTh ; K_x[:, :12] = P_inv[:, :12] HTH   (esekfom.hpp:1727-1729) */
+    gj_solve(ex, w->M1, 12, 25, &w->piv, &w->pivval);
     LV_PAR(it, n * 13) {
         const int i = it / 13, j = it - i * 13;
-        const double* pi = w->M2 + i * kAug + n;
         double s = 0;
-        if (j < 12) {
-            for (int k = 0; k < 12; ++k) s += pi[k] * w->HTH[k * 12 + j];
-            w->Kx[i * 12 + j] = s;
-        } else {
-            for (int k = 0; k < 12; ++k) s += pi[k] * w->HTh[k];
-            w->Kh[i] = s;
-        }
+        for (int k = 0; k < 12; ++k) s += w->P[i * n + k] * w->M1[k * 25 + 12 + j];
+        s *= invR;
+        if (j < 12) w->Kx[i * 12 + j] = s; else w->Kh[i] = s;
     }
     ex.sync();
     /* dx_ = K_h + (K_x - I) dx_new   (esekfom.hpp:1733) */

@@ -12,7 +12,7 @@
 
 namespace lv {
 
-enum { kMeasureThreads = 128, kPartialStride = 96, kStepThreads = 512 };
+enum { kMeasureThreads = 128, kPartialStride = 96, kStepThreads = 256 };
 
 /* per-launch constants of the fused measure kernel */
 struct MeasureArgs {
@@ -35,6 +35,17 @@ struct MeasureArgs {
     float* dist;
     float* g_world;
     double* rows;              /* n x 13 (row[12], h)                                     */
+    int4* nn_a;                /* n: search result handed from K1 to K2 (neighbours 0..3)      */
+    int2* nn_b;                /* n: (neighbour 4, bits of the 5th squared distance)         */
+    uint32_t* hard_list;       /* n: queries level 0 could not certify (K1 -> K1b)           */
+    uint32_t* hard_count;
+};
+
+/* one level of the voxel pyramid */
+struct MapLevel {
+    uint4* table;              /* hash slots (2 x uint4 each), grown on demand             */
+    uint64_t table_cap;        /* allocated uint4 elements                                 */
+    uint32_t mask;             /* slots in use - 1                                         */
 };
 
 /* device map storage + scratch for the per-sweep rebuild */
@@ -46,14 +57,18 @@ struct MapBuffers {
     uint64_t* keys_sorted;     /* cap */
     uint32_t* vals;
     uint32_t* vals_sorted;
-    float4* pts;               /* cap, sorted by voxel key                                 */
-    uint4* table;              /* table_cap slots                                          */
-    uint32_t table_cap;        /* allocated slots (power of two)                           */
-    uint32_t table_mask;       /* slots in use - 1                                         */
-    uint32_t* counter;         /* device scalar                                            */
+    float4* pts;               /* cap, Morton-sorted                                       */
+    MapLevel level[kMaxLevels];
+    int32_t n_levels;
+    float4* halo;              /* level-0 halo buckets, grown on demand                    */
+    uint64_t halo_cap, halo_n;
+    uint32_t* bsize;           /* per level-0 slot: halo bucket size / offset              */
+    uint32_t* bstart;
+    uint64_t bs_cap, bs_cap2;
+    uint32_t* counter;         /* device scalars                                           */
     void* sort_tmp;
     size_t sort_tmp_bytes;
-    float cell, inv_cell;
+    float cell, inv_cell;      /* finest level                                             */
 };
 
 size_t map_sort_tmp_bytes(int64_t cap);

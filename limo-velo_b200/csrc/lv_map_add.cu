@@ -27,12 +27,16 @@
 namespace lv {
 
 LV_HD int fine_coord(float v, float ds) { return (int)floorf(fdiv(v, ds)); }   /* ikd_Tree.cpp:493 */
+LV_HD uint64_t fine_key(int ix, int iy, int iz) {   /* any injective key of the downsample voxel */
+    return ((uint64_t)(uint32_t)(iz + LV_KEY_BIAS) << 42) | ((uint64_t)(uint32_t)(iy + LV_KEY_BIAS) << 21) |
+           (uint64_t)(uint32_t)(ix + LV_KEY_BIAS);
+}
 
 __global__ void __launch_bounds__(256) lv_add_keys_kernel(const float* __restrict__ xyz, int64_t total, float ds,
                                                            uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    keys[i] = voxel_key(fine_coord(xyz[3 * i], ds), fine_coord(xyz[3 * i + 1], ds), fine_coord(xyz[3 * i + 2], ds));
+    keys[i] = fine_key(fine_coord(xyz[3 * i], ds), fine_coord(xyz[3 * i + 1], ds), fine_coord(xyz[3 * i + 2], ds));
     vals[i] = (uint32_t)i;
 }
 

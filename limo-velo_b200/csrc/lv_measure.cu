@@ -9,13 +9,17 @@
  *   Localizator::calculate_H      src/Modules/Localizator.cpp:29-57
  * and the reduction IKFoM performs on its output,
  *   HTH = h_x^T h_x, h_x^T h      esekfom.hpp:1723,1727
+ * Two kernels per evaluation: K1 lv_search_kernel (exact 5-NN, thin, maximum occupancy) hands 24 B
+ * per query (neighbour positions + 5th distance) to K2 lv_fit_kernel (plane fit, row, reduction).
  * H (Nm x 12 fp64) is never materialised: every thread produces its row in registers, rows are
  * staged once in shared memory and folded into the 78 + 12 unique sums per block, in a fixed
- * order (deterministic).  One block = kMeasureThreads queries per tile, grid-stride over tiles.
+ * order (deterministic).
  *
  * Bound: HBM/L2 gather latency: algorithmic traffic is 72 B per point (12 B query +
  * 5 x 12 B neighbours), no tensor-core-shaped work.
  */
+#include <stdlib.h>
+
 #include "lv_internal.h"
 
 namespace lv {
@@ -39,9 +43,85 @@ static void init_pairs() {
 }
 
 #define LV_ROW_STRIDE (kMeasureThreads + 1)   /* +1 double: 13 row-columns land in distinct banks */
+#define LV_SEARCH_THREADS 128
+#define LV_GROUP 4                              /* lanes per query in K1 (LV_SEARCH_GROUP=1|2|4|8 overrides) */
 
-__global__ void __launch_bounds__(kMeasureThreads) lv_measure_kernel(const MeasureArgs a) {
+__device__ __forceinline__ void store_neighbours(const MeasureArgs& a, int qi, const Top5& t, bool in_pts) {
+    int4 o;
+    int i4 = t.i4;
+    o.x = t.i0; o.y = t.i1; o.z = t.i2; o.w = t.i3;
+    if (in_pts) {   /* positions p in pts[] are stored as -2 - p, positions in halo[] as they are, -1 = none */
+        o.x = o.x < 0 ? -1 : -2 - o.x; o.y = o.y < 0 ? -1 : -2 - o.y; o.z = o.z < 0 ? -1 : -2 - o.z;
+        o.w = o.w < 0 ? -1 : -2 - o.w; i4 = i4 < 0 ? -1 : -2 - i4;
+    }
+    a.nn_a[qi] = o;
+    a.nn_b[qi] = make_int2(i4, __float_as_int(t.d4));
+}
+
+/*
+ * K1 — search, level 0.  G lanes per query, ONE query per lane group, so the grid holds N * G / 32
+ * warps and every SM keeps its full complement of warps in flight: the search is a chain of dependent
+ * memory round trips (point -> hash slot -> halo bucket) and only resident warps hide them.  The
+ * kernel is thin (no plane fit, ~50 registers).  Per group: one hash probe (all lanes, same address),
+ * one contiguous scan of the home voxel's halo bucket (a request of the G lanes covers G x 16
+ * contiguous bytes), shuffle merge, certification.  Queries level 0 cannot certify (sparse spot, no
+ * slot) are appended to a work list for K1b.
+ * History (ncu r1a..r1e + clock64 phase timers, profiles/): fused with the fit at 127 registers the
+ * search phase alone cost 36-60 k cycles per 128-query tile; hard queries finished inside the warp
+ * that found them serialised up to 13 ring searches in one warp (firing order clusters them).
+ * Output, 24 B per query: positions of the 5 neighbours and the 5th squared distance.
+ */
+template <int G>
+__global__ void __launch_bounds__(LV_SEARCH_THREADS) lv_search_kernel(const MeasureArgs a) {
     if (a.ctrl->done) return;   /* update already finished (uniform over the grid) */
+    typedef GroupLanes<G> Grp;
+    const Rt32& T = a.ctrl->frame.lidar_to_world;       /* uniform loads */
+    const int qi = (int)(((int64_t)blockIdx.x * LV_SEARCH_THREADS + threadIdx.x) / G);
+    const bool have = qi < a.n;
+    float g[3] = {0.f, 0.f, 0.f};
+    uint32_t bs = 0, bc = 0;
+    int st = 0;                       /* 0 no query / not finite, 1 bucket, 2 no level-0 slot */
+    if (have) {
+        rt_apply(T, a.xyz[3 * qi], a.xyz[3 * qi + 1], a.xyz[3 * qi + 2], g);   /* Mapper.cpp:51 */
+        const bool finite = (fabsf(g[0]) < 1e9f) && (fabsf(g[1]) < 1e9f) && (fabsf(g[2]) < 1e9f);
+        if (finite) st = level0_probe(a.map, g[0], g[1], g[2], &bs, &bc) ? 1 : 2;
+    }
+    Top5 t;
+    const bool settled = level0_scan<Grp>(a.map, g[0], g[1], g[2], a.max_d2, bs, bc, st == 1, t);
+    if (have && (threadIdx.x & (G - 1)) == 0) {
+        store_neighbours(a, qi, t, false);
+        if (st == 2 || (st == 1 && !settled)) a.hard_list[atomicAdd(a.hard_count, 1u)] = (uint32_t)qi;
+    }
+}
+
+/*
+ * K1b — search, upper levels: one WARP per query K1 could not certify (knn5_upper).  The work list
+ * length lives on the device; a fixed grid strides over it, so no host round trip is needed.
+ */
+__global__ void __launch_bounds__(128) lv_search_upper_kernel(const MeasureArgs a) {
+    if (a.ctrl->done) return;
+    const uint32_t n_hard = *a.hard_count;
+    const Rt32& T = a.ctrl->frame.lidar_to_world;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t h = warp; h < n_hard; h += n_warps) {
+        const int qi = (int)a.hard_list[h];
+        float g[3];
+        rt_apply(T, a.xyz[3 * qi], a.xyz[3 * qi + 1], a.xyz[3 * qi + 2], g);
+        const int2 prev = a.nn_b[qi];   /* level 0's (uncertified) 5th distance bounds the answer from above */
+        Top5 u;
+        knn5_upper<GroupWarp>(a.map, g[0], g[1], g[2], a.max_d2, prev.x >= 0 ? __int_as_float(prev.y) : a.max_d2, u);
+        if ((threadIdx.x & 31) == 0) store_neighbours(a, qi, u, true);
+    }
+}
+
+/*
+ * K2 — fit, row, reduce.  One thread per query, one tile = kMeasureThreads queries.
+ *   fit + row   gates (Plane.cpp:36-43), 5x3 QR plane fit, residual, Jacobian row
+ *   reduce      the 90 unique sums of H^T H and H^T h over the tile, fixed order; H (Nm x 12 fp64) is
+ *               never materialised
+ */
+__global__ void __launch_bounds__(kMeasureThreads) lv_fit_kernel(const MeasureArgs a) {
+    if (a.ctrl->done) return;
 
     __shared__ Frame s_frame;
     __shared__ double s_rows[13 * LV_ROW_STRIDE];
@@ -62,44 +142,49 @@ __global__ void __launch_bounds__(kMeasureThreads) lv_measure_kernel(const Measu
         bool chosen = false;
         double row[12], hval = 0.0;
         if (i < a.n) {
-            const float px = a.xyz[3 * i], py = a.xyz[3 * i + 1], pz = a.xyz[3 * i + 2];
             float g[3];
-            rt_apply(s_frame.lidar_to_world, px, py, pz, g);                  /* Mapper.cpp:51 */
-            Top5 t;
-            top5_init(t, a.max_d2);
-            const bool finite = (fabsf(g[0]) < 1e9f) && (fabsf(g[1]) < 1e9f) && (fabsf(g[2]) < 1e9f);
-            if (finite) knn5(a.map, g[0], g[1], g[2], a.max_d2, a.max_ring, t);
+            rt_apply(s_frame.lidar_to_world, a.xyz[3 * i], a.xyz[3 * i + 1], a.xyz[3 * i + 2], g);
+            const int4 na = a.nn_a[i];
+            const int2 nb = a.nn_b[i];
+            const float d4 = __int_as_float(nb.y);
             float abcd[4] = {0.f, 0.f, 0.f, 0.f};
             float dist = 0.f;
-            /* Plane.cpp:36-43: 5 neighbours and the farthest closer than MAX_DIST_PLANE */
-            if (t.i4 >= 0 && (double)t.d4 < a.gate_d2) {
-                float q[5][3];
-                const float4 q0 = load_point(a.map.pts + t.i0), q1 = load_point(a.map.pts + t.i1),
-                             q2 = load_point(a.map.pts + t.i2), q3 = load_point(a.map.pts + t.i3),
-                             q4 = load_point(a.map.pts + t.i4);
+            float q[5][3];
+            float dsq[5] = {INFINITY, INFINITY, INFINITY, INFINITY, INFINITY};
+            int orig[5] = {-1, -1, -1, -1, -1};
+            const bool full = nb.x != -1;
+            if (full) {
+                const bool general = nb.x < -1;      /* found by the upper-level search: positions in pts[] */
+                const float4* src = general ? a.map.pts : a.map.halo;
+                const float4 q0 = load_point(src + (general ? -2 - na.x : na.x)), q1 = load_point(src + (general ? -2 - na.y : na.y)),
+                             q2 = load_point(src + (general ? -2 - na.z : na.z)), q3 = load_point(src + (general ? -2 - na.w : na.w)),
+                             q4 = load_point(src + (general ? -2 - nb.x : nb.x));
                 q[0][0] = q0.x; q[0][1] = q0.y; q[0][2] = q0.z;
                 q[1][0] = q1.x; q[1][1] = q1.y; q[1][2] = q1.z;
                 q[2][0] = q2.x; q[2][1] = q2.y; q[2][2] = q2.z;
                 q[3][0] = q3.x; q[3][1] = q3.y; q[3][2] = q3.z;
                 q[4][0] = q4.x; q[4][1] = q4.y; q[4][2] = q4.z;
-                chosen = plane_fit(q, a.planes_threshold, abcd);               /* Plane.cpp:45-55 */
-                if (chosen) {
-                    dist = plane_dist(abcd, g);                                /* Match.cpp:21 */
-                    jacobian_row(s_frame, g, abcd, dist, a.estimate_extrinsics != 0, row, &hval);
-                } else {
-                    abcd[0] = abcd[1] = abcd[2] = abcd[3] = 0.f;
+                orig[0] = __float_as_int(q0.w); orig[1] = __float_as_int(q1.w); orig[2] = __float_as_int(q2.w);
+                orig[3] = __float_as_int(q3.w); orig[4] = __float_as_int(q4.w);
+                /* Plane.cpp:36-43: 5 neighbours and the farthest closer than MAX_DIST_PLANE */
+                if ((double)d4 < a.gate_d2) {
+                    chosen = plane_fit(q, a.planes_threshold, abcd);               /* Plane.cpp:45-55 */
+                    if (chosen) {
+                        dist = plane_dist(abcd, g);                                /* Match.cpp:21 */
+                        jacobian_row(s_frame, g, abcd, dist, a.estimate_extrinsics != 0, row, &hval);
+                    } else {
+                        abcd[0] = abcd[1] = abcd[2] = abcd[3] = 0.f;
+                    }
                 }
             }
             if (a.valid) a.valid[i] = chosen ? 1 : 0;
             if (a.g_world) { a.g_world[3 * i] = g[0]; a.g_world[3 * i + 1] = g[1]; a.g_world[3 * i + 2] = g[2]; }
             if (a.nn_idx || a.nn_sqd) {
-                const int ids[5] = {t.i0, t.i1, t.i2, t.i3, t.i4};
-                const float ds[5] = {t.d0, t.d1, t.d2, t.d3, t.d4};
-                const bool full = t.i4 >= 0;
+                if (full)
+                    for (int k = 0; k < 5; ++k) dsq[k] = sq_dist(g[0], g[1], g[2], q[k][0], q[k][1], q[k][2]);
                 for (int k = 0; k < 5; ++k) {
-                    if (a.nn_idx)
-                        a.nn_idx[5 * i + k] = full ? __float_as_int(load_point(a.map.pts + ids[k]).w) : -1;
-                    if (a.nn_sqd) a.nn_sqd[5 * i + k] = full ? ds[k] : INFINITY;
+                    if (a.nn_idx) a.nn_idx[5 * i + k] = orig[k];
+                    if (a.nn_sqd) a.nn_sqd[5 * i + k] = dsq[k];
                 }
             }
             if (a.plane) { for (int k = 0; k < 4; ++k) a.plane[4 * i + k] = abcd[k]; }
@@ -109,7 +194,7 @@ __global__ void __launch_bounds__(kMeasureThreads) lv_measure_kernel(const Measu
                 a.rows[13 * (size_t)i + 12] = chosen ? hval : 0.0;
             }
         }
-        /* stage the row (zeros when rejected) and fold the tile into the block's 90 sums */
+        /* stage the row (zeros when rejected), fold the tile into the block's 90 sums */
 #pragma unroll
         for (int k = 0; k < 12; ++k) s_rows[k * LV_ROW_STRIDE + tid] = chosen ? row[k] : 0.0;
         s_rows[12 * LV_ROW_STRIDE + tid] = chosen ? hval : 0.0;
@@ -141,7 +226,22 @@ __device__ void reduce_partials_block(const double* partials, int n_partials, do
                                       double* HTH, double* HTh, int64_t* nm) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     double a0 = 0, a1 = 0, a2 = 0;
-    for (int b = warp; b < n_partials; b += nwarps) {
+    int b = warp;
+    for (; b + 3 * nwarps < n_partials; b += 4 * nwarps) {   /* 12 independent loads in flight, fixed order of adds */
+        const double* p0 = partials + (size_t)b * kPartialStride;
+        const double* p1 = p0 + (size_t)nwarps * kPartialStride;
+        const double* p2 = p1 + (size_t)nwarps * kPartialStride;
+        const double* p3 = p2 + (size_t)nwarps * kPartialStride;
+        const double x0 = p0[lane], y0 = p0[lane + 32], z0 = p0[lane + 64];
+        const double x1 = p1[lane], y1 = p1[lane + 32], z1 = p1[lane + 64];
+        const double x2 = p2[lane], y2 = p2[lane + 32], z2 = p2[lane + 64];
+        const double x3 = p3[lane], y3 = p3[lane + 32], z3 = p3[lane + 64];
+        a0 += x0; a1 += y0; a2 += z0;
+        a0 += x1; a1 += y1; a2 += z1;
+        a0 += x2; a1 += y2; a2 += z2;
+        a0 += x3; a1 += y3; a2 += z3;
+    }
+    for (; b < n_partials; b += nwarps) {
         const double* p = partials + (size_t)b * kPartialStride;
         a0 += p[lane];
         a1 += p[lane + 32];
@@ -216,7 +316,23 @@ int measure_grid(int n) {
 
 cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st) {
     init_pairs();
-    lv_measure_kernel<<<grid, kMeasureThreads, 0, st>>>(a);
+    static int group = 0;   /* lanes per query in K1; LV_SEARCH_GROUP overrides for tuning runs */
+    if (!group) {
+        const char* e = getenv("LV_SEARCH_GROUP");
+        group = e ? atoi(e) : LV_GROUP;
+        if (group != 1 && group != 2 && group != 4 && group != 8) group = LV_GROUP;
+    }
+    int sgrid = (int)(((int64_t)a.n * group + LV_SEARCH_THREADS - 1) / LV_SEARCH_THREADS);
+    if (sgrid < 1) sgrid = 1;
+    cudaMemsetAsync(a.hard_count, 0, sizeof(uint32_t), st);
+    switch (group) {
+        case 1: lv_search_kernel<1><<<sgrid, LV_SEARCH_THREADS, 0, st>>>(a); break;
+        case 2: lv_search_kernel<2><<<sgrid, LV_SEARCH_THREADS, 0, st>>>(a); break;
+        case 8: lv_search_kernel<8><<<sgrid, LV_SEARCH_THREADS, 0, st>>>(a); break;
+        default: lv_search_kernel<4><<<sgrid, LV_SEARCH_THREADS, 0, st>>>(a); break;
+    }
+    lv_search_upper_kernel<<<148 * 2, 128, 0, st>>>(a);
+    lv_fit_kernel<<<grid, kMeasureThreads, 0, st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_ieskf_begin(UpdateCtrl* c, cudaStream_t st) {

@@ -9,16 +9,26 @@
  * identical neighbour sets for every point the reference can accept, "fewer than 5" otherwise.
  *
  * Map layout in HBM (built by lv_map_build.cu once per sweep, replacing the pointer-linked
- * kd-tree of ikd_Tree.h:66-89):
- *   pts[]    float4 (x, y, z, bits(map index)), sorted by voxel key -> each voxel's points are
- *            one contiguous, 16-byte aligned run (one or two 128-byte lines for a typical voxel)
- *   table[]  open-addressing hash table, one 16-byte slot per occupied voxel:
- *            {key_lo, key_hi, start, count}; empty slot = key 0xFFFFFFFFFFFFFFFF
- * Voxel edge c (lv_params.voxel_size, default 0.5 m).  Search: visit the query's own voxel, then
- * shells of Chebyshev radius r = 1, 2, ... ; a voxel is probed only if its box distance to the
- * query is smaller than the current 5th best (the kd-tree's pruning rule, ikd_Tree.cpp:1098,
- * applied to voxels); stop as soon as the 5th best is within the radius certified by the
- * completed shells, or that radius reaches MAX_DIST_PLANE.
+ * kd-tree of ikd_Tree.h:66-89): a pyramid of hashed voxel grids over ONE Morton-sorted point array.
+ *   pts[]      float4 (x, y, z, bits(map index)) sorted by the 63-bit Morton code of the finest
+ *              voxel coordinates; the voxel of level l (edge c * 2^l) is the code >> 3l, so every
+ *              voxel of every level is one contiguous run of pts[]
+ *   level l    table_l[]  open-addressing hash, one 32-byte slot (= one DRAM/L2 sector) per
+ *                         voxel: {key_lo, key_hi, start, count | halo_start, halo_count, -, -}
+ *   level 0    additionally holds a slot (count 0) for every EMPTY voxel adjacent to an occupied
+ *              one, and halo[]: "halo buckets" — for every level-0 slot one contiguous run with
+ *              the voxel's own points followed by those of its (up to 26) occupied neighbours
+ * The coarsest level has an edge >= MAX_DIST_PLANE.
+ *
+ * Search: at level 0, one thread per query (knn5_level0): ONE probe finds the home voxel and ONE
+ * contiguous scan of its halo bucket sees every map point within Chebyshev ring 1, i.e. within the
+ * certified radius (edge + distance to the nearest face) of the query.  If the 5th best lies
+ * inside that radius the answer is exact and final (the bulk of a sweep).  Otherwise — sparse spot,
+ * or a query more than a voxel away from the map — a whole warp searches ring 1 of the coarser
+ * levels (knn5_upper), the lanes sharing probes and striding over the voxel runs.  At the coarsest
+ * level the certified radius covers the whole search ball, so the answer is always exact.  No tree
+ * descent, no data-dependent ring loops: the pointer chasing of the kd-tree becomes a streaming
+ * read, paid for with ~30x the map in HBM for the level-0 halo of a surface-like map.
  */
 #ifndef LV_VOXEL_SEARCH_H_
 #define LV_VOXEL_SEARCH_H_
@@ -32,31 +42,68 @@ struct uint4 { unsigned int x, y, z, w; };
 
 namespace lv {
 
+enum { kMaxLevels = 4 };
+
+struct VoxelLevel {
+    const uint4* table;     /* hash slots, 2 x uint4 each          */
+    uint32_t mask;          /* slots - 1                           */
+    float cell;             /* voxel edge of this level            */
+};
+
 struct VoxelMapView {
-    const float4* pts;      /* sorted points */
-    const uint4* table;     /* hash slots    */
-    uint32_t mask;          /* capacity - 1  */
+    const float4* pts;      /* Morton-sorted points                */
+    const float4* halo;     /* halo buckets of level 0             */
+    VoxelLevel lv[kMaxLevels];
+    int32_t n_levels;
     uint32_t n_points;
-    float cell;             /* voxel edge                        */
-    float inv_cell;         /* 1 / cell (fp32, used identically for build and query) */
+    float cell0;            /* finest voxel edge                   */
+    float inv_cell0;        /* 1 / cell0 (fp32, used identically for build and query) */
 };
 
 #define LV_KEY_BIAS (1 << 20)
 #define LV_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
 
-LV_HD int voxel_coord(float v, float inv_cell) { return (int)floorf(fmul(v, inv_cell)); }
-
-LV_HD uint64_t voxel_key(int ix, int iy, int iz) {
-    return ((uint64_t)(uint32_t)(iz + LV_KEY_BIAS) << 42) | ((uint64_t)(uint32_t)(iy + LV_KEY_BIAS) << 21) |
-           (uint64_t)(uint32_t)(ix + LV_KEY_BIAS);
+/* biased (non-negative, 21-bit) finest-level voxel coordinate */
+LV_HD uint32_t voxel_coord(float v, float inv_cell0) {
+    int c = (int)floorf(fmul(v, inv_cell0)) + LV_KEY_BIAS;
+    c = c < 0 ? 0 : (c > 0x1FFFFF ? 0x1FFFFF : c);
+    return (uint32_t)c;
 }
-LV_HD uint32_t voxel_hash(uint64_t k) {
-    k ^= k >> 33;
-    k *= 0xff51afd7ed558ccdull;
-    k ^= k >> 33;
-    k *= 0xc4ceb9fe1a85ec53ull;
-    k ^= k >> 33;
-    return (uint32_t)k;
+LV_HD uint64_t spread21(uint64_t x) {
+    x &= 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+LV_HD uint32_t compact21(uint64_t x) {
+    x &= 0x1249249249249249ull;
+    x = (x ^ (x >> 2)) & 0x10c30c30c30c30c3ull;
+    x = (x ^ (x >> 4)) & 0x100f00f00f00f00full;
+    x = (x ^ (x >> 8)) & 0x1f0000ff0000ffull;
+    x = (x ^ (x >> 16)) & 0x1f00000000ffffull;
+    x = (x ^ (x >> 32)) & 0x1fffffull;
+    return (uint32_t)x;
+}
+/* Morton code of biased voxel coordinates (any level) */
+LV_HD uint64_t morton3(uint32_t bx, uint32_t by, uint32_t bz) { return spread21(bx) | (spread21(by) << 1) | (spread21(bz) << 2); }
+
+/* table key of a voxel given its biased coordinates at that level: any injective packing will do
+ * (the Morton order only matters for the sort); this one costs a handful of instructions */
+LV_HD uint64_t voxel_key(uint32_t bx, uint32_t by, uint32_t bz) { return (uint64_t)bx | ((uint64_t)by << 21) | ((uint64_t)bz << 42); }
+/* the key of the level-l voxel containing the point with Morton code m at the finest level */
+LV_HD uint64_t voxel_key_from_morton(uint64_t m, int l) {
+    return voxel_key(compact21(m) >> l, compact21(m >> 1) >> l, compact21(m >> 2) >> l);
+}
+LV_HD uint32_t voxel_hash(uint64_t k) {   /* classic spatial hash of the three coordinates + a finaliser */
+    uint32_t h = ((uint32_t)k & 0x1FFFFFu) * 73856093u ^ ((uint32_t)(k >> 21) & 0x1FFFFFu) * 19349663u ^
+                 ((uint32_t)(k >> 42) & 0x1FFFFFu) * 83492791u;
+    h ^= h >> 15;
+    h *= 0x2c1b3c6du;
+    h ^= h >> 12;
+    return h;
 }
 
 LV_HD uint4 load_slot(const uint4* p) {
@@ -74,20 +121,19 @@ LV_HD float4 load_point(const float4* p) {
 #endif
 }
 
-/* returns count (0 if the voxel is empty) and its first point index in *start */
-LV_HD uint32_t voxel_lookup(const VoxelMapView& m, int ix, int iy, int iz, uint32_t* start) {
-    const uint64_t key = voxel_key(ix, iy, iz);
+/* slot index of the voxel with table key `key` (voxel_key) in level L, or -1 */
+LV_HD int voxel_find(const VoxelLevel& L, uint64_t key, uint32_t* start, uint32_t* count) {
     const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
-    uint32_t slot = voxel_hash(key) & m.mask;
+    uint32_t slot = voxel_hash(key) & L.mask;
     for (;;) {
-        const uint4 e = load_slot(m.table + slot);
-        if (e.x == klo && e.y == khi) { *start = e.z; return e.w; }
-        if ((e.x & e.y) == 0xFFFFFFFFu) return 0;
-        slot = (slot + 1) & m.mask;
+        const uint4 e = load_slot(L.table + 2 * (size_t)slot);
+        if (e.x == klo && e.y == khi) { *start = e.z; *count = e.w; return (int)slot; }
+        if ((e.x & e.y) == 0xFFFFFFFFu) { *count = 0; return -1; }
+        slot = (slot + 1) & L.mask;
     }
 }
 
-/* ascending top-5 kept in registers.  id = position in the sorted point array (-1 = none). */
+/* ascending top-5 kept in registers.  id = position in the scanned array (-1 = none). */
 struct Top5 {
     float d0, d1, d2, d3, d4;
     int i0, i1, i2, i3, i4;
@@ -100,86 +146,290 @@ LV_HD void top5_init(Top5& t, float bound) {
  * equal distances keep the earlier candidate in front.                                      */
 LV_HD void top5_insert(Top5& t, float d, int id) {
     if (!(d < t.d4)) return;
-    if (d < t.d3) {
-        t.d4 = t.d3; t.i4 = t.i3;
-        if (d < t.d2) {
-            t.d3 = t.d2; t.i3 = t.i2;
-            if (d < t.d1) {
-                t.d2 = t.d1; t.i2 = t.i1;
-                if (d < t.d0) { t.d1 = t.d0; t.i1 = t.i0; t.d0 = d; t.i0 = id; }
-                else { t.d1 = d; t.i1 = id; }
-            } else { t.d2 = d; t.i2 = id; }
-        } else { t.d3 = d; t.i3 = id; }
-    } else { t.d4 = d; t.i4 = id; }
+    /* branch-free bubble through the sorted list: every lane of a warp executes the same selects */
+    bool s;
+    float td; int ti;
+    s = d < t.d0; td = s ? t.d0 : d; ti = s ? t.i0 : id; t.d0 = s ? d : t.d0; t.i0 = s ? id : t.i0; d = td; id = ti;
+    s = d < t.d1; td = s ? t.d1 : d; ti = s ? t.i1 : id; t.d1 = s ? d : t.d1; t.i1 = s ? id : t.i1; d = td; id = ti;
+    s = d < t.d2; td = s ? t.d2 : d; ti = s ? t.i2 : id; t.d2 = s ? d : t.d2; t.i2 = s ? id : t.i2; d = td; id = ti;
+    s = d < t.d3; td = s ? t.d3 : d; ti = s ? t.i3 : id; t.d3 = s ? d : t.d3; t.i3 = s ? id : t.i3; d = td; id = ti;
+    t.d4 = d; t.i4 = id;   /* d < old d4 is known: whatever falls out of slot 3 (or the new value) is the new 5th */
 }
 
-LV_HD void scan_voxel(const VoxelMapView& m, int ix, int iy, int iz, float gx, float gy, float gz, Top5& t) {
-    uint32_t start;
-    const uint32_t cnt = voxel_lookup(m, ix, iy, iz, &start);
-    for (uint32_t j = 0; j < cnt; ++j) {
-        const float4 q = load_point(m.pts + start + j);
-        top5_insert(t, sq_dist(gx, gy, gz, q.x, q.y, q.z), (int)(start + j));
+/* scan `n` consecutive points starting at p; ids are base + j */
+LV_HD void scan_run(const float4* p, uint32_t n, int base, float gx, float gy, float gz, Top5& t) {
+    uint32_t j = 0;
+    for (; j + 4 <= n; j += 4) {   /* four independent 16-byte loads in flight, then the insertions */
+        const float4 q0 = load_point(p + j), q1 = load_point(p + j + 1), q2 = load_point(p + j + 2), q3 = load_point(p + j + 3);
+        top5_insert(t, sq_dist(gx, gy, gz, q0.x, q0.y, q0.z), base + (int)j);
+        top5_insert(t, sq_dist(gx, gy, gz, q1.x, q1.y, q1.z), base + (int)j + 1);
+        top5_insert(t, sq_dist(gx, gy, gz, q2.x, q2.y, q2.z), base + (int)j + 2);
+        top5_insert(t, sq_dist(gx, gy, gz, q3.x, q3.y, q3.z), base + (int)j + 3);
+    }
+    for (; j < n; ++j) {
+        const float4 q = load_point(p + j);
+        top5_insert(t, sq_dist(gx, gy, gz, q.x, q.y, q.z), base + (int)j);
     }
 }
 
-/* distance from the query (offsets lo/hi to the faces of its home voxel) to the near face of the
- * voxel d steps away along one axis, reduced by `slack` so that fp32 rounding of the voxel
- * assignment (floor(v * inv_cell)) can never make the bound optimistic.                      */
-LV_HD float axis_gap(int d, float lo, float hi, float c, float slack) {
-    if (d == 0) return 0.f;
-    const float g = (d > 0 ? (float)(d - 1) * c + hi : (float)(-d - 1) * c + lo) - slack;
-    return g > 0.f ? g : 0.f;
+LV_HD void top5_pop(Top5& t, float bound) {
+    t.d0 = t.d1; t.i0 = t.i1;
+    t.d1 = t.d2; t.i1 = t.i2;
+    t.d2 = t.d3; t.i2 = t.i3;
+    t.d3 = t.d4; t.i3 = t.i4;
+    t.d4 = bound; t.i4 = -1;
+}
+
+/* ---- lane groups: the rare queries level 0 cannot settle are finished by a whole warp ---------- */
+struct GroupSerial {   /* host / single lane */
+    enum { size = 1 };
+    LV_HD static int lane() { return 0; }
+    LV_HD static uint32_t bcast(uint32_t v, int src) { (void)src; return v; }
+    LV_HD static void merge(Top5& loc, float bound, Top5& out) { out = loc; (void)bound; }
+};
+#if defined(__CUDACC__)
+template <int G>
+struct GroupLanes {    /* G consecutive lanes of a warp (G = 8 or 32); every lane of the WARP must call merge() */
+    enum { size = G };
+    __device__ __forceinline__ static int lane() { return (int)(threadIdx.x & (G - 1)); }
+    __device__ __forceinline__ static uint32_t bcast(uint32_t v, int src) {
+        return __shfl_sync(0xffffffffu, v, (int)((threadIdx.x & 31u) & ~(unsigned)(G - 1)) + src);
+    }
+    /* group-wide ascending top-5 of the union of the lanes' lists -> out (identical in all lanes) */
+    __device__ __forceinline__ static void merge(Top5& loc, float bound, Top5& out) {
+        const int l = lane();
+        const unsigned gbase = (threadIdx.x & 31u) & ~(unsigned)(G - 1);
+        float od[5];
+        int oi[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            float m = loc.d0;
+#pragma unroll
+            for (int s = 1; s < G; s <<= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, s));
+            unsigned b = __ballot_sync(0xffffffffu, loc.d0 == m) >> gbase;
+            if (G < 32) b &= (1u << G) - 1u;
+            const int winner = __ffs(b) - 1;                       /* lowest lane on ties */
+            od[k] = m;
+            oi[k] = __shfl_sync(0xffffffffu, loc.i0, (int)gbase + winner);
+            if (l == winner) top5_pop(loc, bound);
+        }
+        out.d0 = od[0]; out.d1 = od[1]; out.d2 = od[2]; out.d3 = od[3]; out.d4 = od[4];
+        out.i0 = oi[0]; out.i1 = oi[1]; out.i2 = oi[2]; out.i3 = oi[3]; out.i4 = oi[4];
+    }
+};
+typedef GroupLanes<32> GroupWarp;
+#endif
+
+/* the query inside its home voxel of level l: distances to the six faces, minus `slack` (a few ulp
+ * of the largest coordinate: fp32 rounding of the voxel assignment floor(v * inv_cell) can never
+ * make a bound optimistic) */
+struct HomeGeom {
+    float lo[3], hi[3];     /* distance to the low / high face per axis, >= 0 */
+    float edge;
+    float slack;
+};
+LV_HD HomeGeom home_geom(const VoxelMapView& m, int l, uint32_t bx0, uint32_t by0, uint32_t bz0, float gx, float gy,
+                         float gz) {
+    HomeGeom h;
+    const float c = m.lv[l].cell;
+    const uint32_t b[3] = {bx0, by0, bz0};
+    const float g[3] = {gx, gy, gz};
+    for (int a = 0; a < 3; ++a) {
+        const float o = ((float)(int)((b[a] >> l) << l) - (float)LV_KEY_BIAS) * m.cell0;   /* low corner */
+        float v = g[a] - o;
+        v = v < 0.f ? 0.f : (v > c ? c : v);
+        h.lo[a] = v;
+        h.hi[a] = c - v;
+    }
+    float amax = fabsf(gx) > fabsf(gy) ? fabsf(gx) : fabsf(gy);
+    amax = amax > fabsf(gz) ? amax : fabsf(gz);
+    h.edge = c;
+    h.slack = 2e-6f * (amax + 4.0f);
+    return h;
+}
+/* squared radius certified once ring 1 of the home voxel has been searched: every other map point
+ * is at least edge + (distance to the nearest face) away */
+LV_HD float certified_d2(const HomeGeom& h) {
+    float gap = h.lo[0] < h.hi[0] ? h.lo[0] : h.hi[0];
+    gap = gap < h.lo[1] ? gap : h.lo[1]; gap = gap < h.hi[1] ? gap : h.hi[1];
+    gap = gap < h.lo[2] ? gap : h.lo[2]; gap = gap < h.hi[2] ? gap : h.hi[2];
+    float cert = h.edge + gap - h.slack;
+    cert = cert > 0.f ? cert : 0.f;
+    return cert * cert;
+}
+/* squared distance from the query to the neighbour voxel (dx, dy, dz) in {-1,0,1}^3, rounded down */
+LV_HD float neighbour_box_d2(const HomeGeom& h, int dx, int dy, int dz) {
+    const int d[3] = {dx, dy, dz};
+    float s = 0.f;
+    for (int a = 0; a < 3; ++a) {
+        float v = d[a] < 0 ? h.lo[a] : (d[a] > 0 ? h.hi[a] : 0.f);
+        v = d[a] == 0 ? 0.f : v - h.slack;
+        v = v > 0.f ? v : 0.f;
+        s += v * v;
+    }
+    return s;
+}
+
+/* where the 5 neighbours of a query were found */
+enum { kSrcHalo = 0, kSrcPts = 1 };   /* ids index halo[] (level 0) or pts[] (upper levels) */
+
+/*
+ * Level 0 in two steps so that a thread block can put ALL its probes and bucket fetches in flight
+ * before anything waits on them.
+ *   level0_probe   one thread per query: ONE hash probe -> the halo bucket (start, count) of the
+ *                  query's home voxel, and an L2 prefetch of every 128-byte line of that bucket.
+ *                  Level-0 slots exist for every occupied voxel AND for every empty voxel adjacent
+ *                  to one, so a query only misses here when it is farther than one voxel from all
+ *                  map points (returns false).
+ *   level0_scan    one GROUP of lanes per query (8 on the device: 8 x 16 B = one 128-byte line per
+ *                  request, so the bucket streams through L1 in full lines; 1 on the host): ONE
+ *                  contiguous scan + one merge.  Returns true when `out` (identical in all lanes of
+ *                  the group) is final, i.e. certified exact.  `active` = the group has a query with a
+ *                  bucket; inactive groups only take part in the collectives.
+ */
+LV_HD bool level0_probe(const VoxelMapView& m, float gx, float gy, float gz, uint32_t* bstart, uint32_t* bcount) {
+    const uint32_t bx0 = voxel_coord(gx, m.inv_cell0), by0 = voxel_coord(gy, m.inv_cell0), bz0 = voxel_coord(gz, m.inv_cell0);
+    uint32_t start, count;
+    const int slot = voxel_find(m.lv[0], voxel_key(bx0, by0, bz0), &start, &count);
+    *bstart = 0;
+    *bcount = 0;
+    if (slot < 0) return false;
+    const uint4 b = load_slot(m.lv[0].table + 2 * (size_t)slot + 1);
+    *bstart = b.x;
+    *bcount = b.y;
+#if defined(__CUDA_ARCH__)
+    {   /* fire-and-forget: the scan that follows finds the bucket in L2 */
+        const char* p = reinterpret_cast<const char*>(m.halo + b.x);
+        const char* e = p + (size_t)(b.y < 192u ? b.y : 192u) * sizeof(float4);
+        for (p = (const char*)((uintptr_t)p & ~(uintptr_t)127); p < e; p += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
+#endif
+    return true;
+}
+
+template <class Grp>
+LV_HD bool level0_scan(const VoxelMapView& m, float gx, float gy, float gz, float max_d2, uint32_t bstart, uint32_t bcount,
+                       bool active, Top5& out) {
+    Top5 loc;
+    top5_init(loc, max_d2);
+    if (active) {
+        const float4* p = m.halo + bstart;
+        const uint32_t n = bcount, step = (uint32_t)Grp::size;
+        uint32_t j = (uint32_t)Grp::lane();
+        for (; j + 3 * step < n; j += 4 * step) {   /* four independent 16-byte loads in flight per lane */
+            const float4 q0 = load_point(p + j), q1 = load_point(p + j + step), q2 = load_point(p + j + 2 * step),
+                         q3 = load_point(p + j + 3 * step);
+            top5_insert(loc, sq_dist(gx, gy, gz, q0.x, q0.y, q0.z), (int)(bstart + j));
+            top5_insert(loc, sq_dist(gx, gy, gz, q1.x, q1.y, q1.z), (int)(bstart + j + step));
+            top5_insert(loc, sq_dist(gx, gy, gz, q2.x, q2.y, q2.z), (int)(bstart + j + 2 * step));
+            top5_insert(loc, sq_dist(gx, gy, gz, q3.x, q3.y, q3.z), (int)(bstart + j + 3 * step));
+        }
+        for (; j < n; j += step) {
+            const float4 q = load_point(p + j);
+            top5_insert(loc, sq_dist(gx, gy, gz, q.x, q.y, q.z), (int)(bstart + j));
+        }
+    }
+    Grp::merge(loc, max_d2, out);
+    if (!active) return false;
+    const uint32_t bx0 = voxel_coord(gx, m.inv_cell0), by0 = voxel_coord(gy, m.inv_cell0), bz0 = voxel_coord(gz, m.inv_cell0);
+    return out.d4 <= certified_d2(home_geom(m, 0, bx0, by0, bz0, gx, gy, gz));   /* out.d4 <= max_d2 always */
+}
+
+/* strided scan: lane `first` of `step` lanes takes points first, first+step, ... */
+LV_HD void scan_run_strided(const float4* p, uint32_t n, int base, uint32_t first, uint32_t step, float gx, float gy,
+                            float gz, Top5& t) {
+    for (uint32_t j = first; j < n; j += step) {
+        const float4 q = load_point(p + j);
+        top5_insert(t, sq_dist(gx, gy, gz, q.x, q.y, q.z), base + (int)j);
+    }
 }
 
 /*
- * Exact 5 nearest map points of g within squared radius max_d2 (exclusive).
- * max_ring = ceil(max_dist / c).  Result ascending in t; t.i4 < 0 means "fewer than 5".
+ * The queries level 0 could not settle, executed by a whole warp on the device (one lane on the
+ * host): ring-1 search on ONE coarser level, chosen so that it is conclusive.
+ *   bound0  squared 5th distance level 0 found among real points (an upper bound of the answer), or
+ *           max_d2 if it found fewer than 5.  The level is the first whose edge >= sqrt(bound0): every
+ *           point that can still matter lies within ring 1 of the query's home voxel there.  With
+ *           bound0 = max_d2 that is the last level (edge >= search radius).
+ *   the lanes probe the 27 voxels (skipping those farther than the bound), a warp scan of the counts
+ *   flattens all their points into one index range that the lanes stride over with independent
+ *   loads (binary search of the prefix sums by shuffles), then one merge.
+ * Ids in `out` index pts[].
  */
-LV_HD void knn5(const VoxelMapView& m, float gx, float gy, float gz, float max_d2, int max_ring, Top5& t) {
-    top5_init(t, max_d2);
-    const float c = m.cell;
-    const int cx = voxel_coord(gx, m.inv_cell), cy = voxel_coord(gy, m.inv_cell), cz = voxel_coord(gz, m.inv_cell);
-    /* offsets of g inside its voxel, clamped to [0, c] against fp rounding of the floor */
-    float lx = gx - (float)cx * c, ly = gy - (float)cy * c, lz = gz - (float)cz * c;
-    lx = lx < 0.f ? 0.f : (lx > c ? c : lx);
-    ly = ly < 0.f ? 0.f : (ly > c ? c : ly);
-    lz = lz < 0.f ? 0.f : (lz > c ? c : lz);
-    const float hx = c - lx, hy = c - ly, hz = c - lz;
-    float gap = lx < hx ? lx : hx;
-    gap = gap < ly ? gap : ly; gap = gap < hy ? gap : hy;
-    gap = gap < lz ? gap : lz; gap = gap < hz ? gap : hz;
-
-    /* a few ulp of the largest coordinate involved (2^-23 ~ 1.2e-7 relative) */
-    float amax = fabsf(gx) > fabsf(gy) ? fabsf(gx) : fabsf(gy);
-    amax = amax > fabsf(gz) ? amax : fabsf(gz);
-    const float slack = 2e-6f * (amax + 4.0f);
-
-    scan_voxel(m, cx, cy, cz, gx, gy, gz, t);
-    for (int r = 1; r <= max_ring; ++r) {
-        /* every unvisited point is at least cert away */
-        float cert = (float)(r - 1) * c + gap - slack;
-        cert = cert > 0.f ? cert : 0.f;
-        const float cert2 = cert * cert;
-        if (t.d4 <= cert2) break;          /* also covers cert2 >= max_d2 (d4 <= max_d2 always) */
-        for (int dz = -r; dz <= r; ++dz) {
-            const float az = axis_gap(dz, lz, hz, c, slack);
-            const float az2 = az * az;
-            if (!(az2 < t.d4)) continue;
-            const bool zface = (dz == -r || dz == r);
-            for (int dy = -r; dy <= r; ++dy) {
-                const float ay = axis_gap(dy, ly, hy, c, slack);
-                const float ayz2 = az2 + ay * ay;
-                if (!(ayz2 < t.d4)) continue;
-                const bool face = zface || dy == -r || dy == r;
-                const int step = face ? 1 : 2 * r;
-                for (int dx = -r; dx <= r; dx += step) {
-                    const float ax = axis_gap(dx, lx, hx, c, slack);
-                    if (!(ayz2 + ax * ax < t.d4)) continue;
-                    scan_voxel(m, cx + dx, cy + dy, cz + dz, gx, gy, gz, t);
-                }
-            }
-        }
+template <class Grp>
+LV_HD void knn5_upper(const VoxelMapView& m, float gx, float gy, float gz, float max_d2, float bound0, Top5& out) {
+    const uint32_t bx0 = voxel_coord(gx, m.inv_cell0), by0 = voxel_coord(gy, m.inv_cell0), bz0 = voxel_coord(gz, m.inv_cell0);
+    const int last = m.n_levels - 1;
+    int l = last > 0 ? 1 : 0;
+    {
+        float amax = fabsf(gx) > fabsf(gy) ? fabsf(gx) : fabsf(gy);
+        amax = amax > fabsf(gz) ? amax : fabsf(gz);
+        const float slack = 2e-6f * (amax + 4.0f);
+        while (l < last && !(bound0 <= (m.lv[l].cell - slack) * (m.lv[l].cell - slack))) ++l;
     }
+    /* strictly above bound0 so that the points level 0 saw are found again */
+    float bound = nextafterf(bound0, INFINITY);
+    bound = bound < max_d2 ? bound : max_d2;
+    const VoxelLevel& L = m.lv[l];
+    const HomeGeom h = home_geom(m, l, bx0, by0, bz0, gx, gy, gz);
+    const int hx = (int)(bx0 >> l), hy = (int)(by0 >> l), hz = (int)(bz0 >> l);
+    Top5 loc;
+    top5_init(loc, bound);
+#if defined(__CUDA_ARCH__)
+    if (Grp::size == 32) {
+        const int lane = Grp::lane();
+        uint32_t s = 0, cnt = 0;
+        if (lane < 27) {
+            const int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
+            const int cx = hx + dx, cy = hy + dy, cz = hz + dz;
+            if (cx >= 0 && cy >= 0 && cz >= 0 && neighbour_box_d2(h, dx, dy, dz) < bound)
+                if (voxel_find(L, voxel_key((uint32_t)cx, (uint32_t)cy, (uint32_t)cz), &s, &cnt) < 0) cnt = 0;
+        }
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t excl = incl - cnt;
+        for (uint32_t j0 = 0; j0 < total; j0 += 128) {           /* four independent loads in flight per lane */
+            uint32_t idx[4];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t j = j0 + 32u * (uint32_t)u + (uint32_t)lane;
+                ok[u] = j < total;
+                /* first voxel whose inclusive prefix exceeds j: binary search over the 32 lanes */
+                int lo = 0;
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const uint32_t v = __shfl_sync(0xffffffffu, incl, lo + step - 1);
+                    if (v <= j) lo += step;
+                }
+                lo = lo > 31 ? 31 : lo;
+                const uint32_t sv = __shfl_sync(0xffffffffu, s, lo), ev = __shfl_sync(0xffffffffu, excl, lo);
+                idx[u] = sv + (j - ev);
+            }
+            float4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q[u] = ok[u] ? load_point(m.pts + idx[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (ok[u]) top5_insert(loc, sq_dist(gx, gy, gz, q[u].x, q[u].y, q[u].z), (int)idx[u]);
+        }
+        Grp::merge(loc, bound, out);
+        return;
+    }
+#endif
+    for (int n = 0; n < 27; ++n) {   /* single-lane form of the same search */
+        const int dx = n % 3 - 1, dy = (n / 3) % 3 - 1, dz = n / 9 - 1;
+        const int cx = hx + dx, cy = hy + dy, cz = hz + dz;
+        uint32_t s, cnt;
+        if (cx < 0 || cy < 0 || cz < 0 || !(neighbour_box_d2(h, dx, dy, dz) < bound)) continue;
+        if (voxel_find(L, voxel_key((uint32_t)cx, (uint32_t)cy, (uint32_t)cz), &s, &cnt) >= 0) scan_run(m.pts + s, cnt, (int)s, gx, gy, gz, loc);
+    }
+    Grp::merge(loc, bound, out);
 }
 
 }  // namespace lv

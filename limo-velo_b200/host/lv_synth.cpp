@@ -214,10 +214,11 @@ int64_t lv_synth_sweep(const lv_synth_world* w, const double* x, int rings, int 
             double range = -1;
             Vec3d dir_body;
             dir_body.x = 1; dir_body.y = 0; dir_body.z = 0;
-            for (int attempt = 0; attempt < 12 && range < 0; ++attempt) {
+            for (int attempt = 0; attempt < 64 && range < 0; ++attempt) {
                 int ring = r;
                 double az = 6.283185307179586 * ((double)a + (attempt ? rng.uni() * azimuths : 0.0)) / azimuths;
                 if (attempt >= 6) ring = (int)(rng.uni() * rings);
+                if (attempt >= 16) ring = (int)(rng.uni() * rings * 0.5);   /* the lower half looks at the ground */
                 const double el = deg * (rings > 1 ? elev_lo_deg + (elev_hi_deg - elev_lo_deg) * ring / (rings - 1) : elev_lo_deg);
                 dir_body.x = cos(el) * cos(az); dir_body.y = cos(el) * sin(az); dir_body.z = sin(el);
                 const Vec3d d = mat3_apply(R, dir_body);

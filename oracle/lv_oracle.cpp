@@ -679,6 +679,7 @@ struct RefIkd {
 RefIkd g_ref;
 
 double g_knn_s = 0, g_total_s = 0;
+int g_threads = 1;   /* OpenMP team of the match loop (Mapper.cpp:45-46: MP_PROC_NUM) */
 inline double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -774,9 +775,9 @@ void match_point(const lvo_map* m, const lvo_params* prm, const Rt32& T, const f
     for (int i = 0; i < 5; ++i) { o->nn_idx[i] = -1; o->nn_sqd[i] = INFINITY; }
     o->abcd[0] = o->abcd[1] = o->abcd[2] = o->abcd[3] = 0;
     o->dist = 0;
-    double t0 = now_s();
+    double t0 = g_threads == 1 ? now_s() : 0.0;
     int found = map_knn(m, o->g, 5, o->nn_idx, o->nn_sqd, nn);
-    g_knn_s += now_s() - t0;
+    if (g_threads == 1) g_knn_s += now_s() - t0;
     o->chosen = false;
     if (found < 5) return;                                                         // Plane.cpp:36-38
     if (!((double)o->nn_sqd[4] < prm->max_dist_plane * prm->max_dist_plane)) return;   // Plane.cpp:40-43
@@ -828,17 +829,36 @@ int measure_reduced(const lvo_map* m, const double* x, const lvo_params* prm, co
     for (int i = 0; i < 144; ++i) HTH[i] = 0;
     for (int i = 0; i < 12; ++i) HTh[i] = 0;
     int64_t cnt = 0;
-    for (int64_t i = 0; i < n; ++i) {
-        MatchOut mt;
-        match_point(m, prm, T, xyz + 3 * i, &mt);
-        if (!mt.chosen) continue;
-        double row[12], h;
-        h_row(x, S, prm, mt, row, &h);
-        for (int a = 0; a < 12; ++a) {
-            for (int b = 0; b < 12; ++b) HTH[a * 12 + b] += row[a] * row[b];
-            HTh[a] += row[a] * h;
+    if (m->backend != LVO_KNN_REF_IKDTREE) map_prepare(m);
+    // Mapper::match runs this loop under "#pragma omp parallel for" with MP_PROC_NUM threads and a racy
+    // shared push_back (Mapper.cpp:45-53); here every thread keeps private sums (order-insensitive to
+    // ~1e-12 relative) that are added in thread order.
+#pragma omp parallel num_threads(g_threads)
+    {
+        double hth[144] = {0}, hthv[12] = {0};
+        int64_t c_local = 0;
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < n; ++i) {
+            MatchOut mt;
+            match_point(m, prm, T, xyz + 3 * i, &mt);
+            if (!mt.chosen) continue;
+            double row[12], h;
+            h_row(x, S, prm, mt, row, &h);
+            for (int a = 0; a < 12; ++a) {
+                for (int b = 0; b < 12; ++b) hth[a * 12 + b] += row[a] * row[b];
+                hthv[a] += row[a] * h;
+            }
+            ++c_local;
         }
-        ++cnt;
+#pragma omp for ordered schedule(static, 1)
+        for (int t = 0; t < g_threads; ++t) {
+#pragma omp ordered
+            {
+                for (int a = 0; a < 144; ++a) HTH[a] += hth[a];
+                for (int a = 0; a < 12; ++a) HTh[a] += hthv[a];
+                cnt += c_local;
+            }
+        }
     }
     *nm = cnt;
     return LVO_OK;
@@ -1437,5 +1457,6 @@ void lvo_plane_fit(const float* pts5, float threshold, float abcd[4], int* is_pl
 void lvo_inverse(const double* A, int n, double* Ainv) { inverse_n(A, n, Ainv); }
 void lvo_sym_eig6(const double* A, double* evals, double* evecs) { sym_eig(A, 6, evals, evecs); }
 void lvo_last_timing(double* knn_s, double* total_s) { *knn_s = g_knn_s; *total_s = g_total_s; }
+void lvo_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
 
 }  // extern "C"

@@ -117,6 +117,8 @@ void lvo_sym_eig6(const double* A, double* evals, double* evecs /*row-major, col
 
 /* timing helper for bench.py: seconds spent inside kNN / rest during the last lvo_update_iterated */
 void lvo_last_timing(double* knn_s, double* total_s);
+/* OpenMP team size of the match loop (MP_PROC_NUM, CMakeLists.txt:19-36); default 1 */
+void lvo_set_threads(int n);
 
 #ifdef __cplusplus
 }

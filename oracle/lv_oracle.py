@@ -309,6 +309,10 @@ def sym_eig6(A):
     return ev, V
 
 
+def set_threads(n):
+    lib().lvo_set_threads(int(n))
+
+
 def last_timing():
     a = C.c_double(0)
     b = C.c_double(0)

@@ -24,7 +24,8 @@ using namespace lv;
 
 struct ShimMap {
     std::vector<float4> pts;
-    std::vector<uint4> table;
+    std::vector<float4> halo;
+    std::vector<uint4> table[kMaxLevels];
     VoxelMapView view;
 };
 
@@ -40,17 +41,30 @@ struct ShimParams {
 
 extern "C" {
 
-ShimMap* shim_map_create(const float* xyz, int64_t m, float cell) {
+static void shim_insert(std::vector<uint4>& tab, uint32_t mask, uint64_t key, uint32_t start, uint32_t count, bool only_if_absent) {
+    uint32_t slot = voxel_hash(key) & mask;
+    for (;;) {
+        uint4& t = tab[2 * (size_t)slot];
+        if ((t.x & t.y) == 0xFFFFFFFFu) { t.x = (uint32_t)key; t.y = (uint32_t)(key >> 32); t.z = start; t.w = count; return; }
+        if (only_if_absent && t.x == (uint32_t)key && t.y == (uint32_t)(key >> 32)) return;
+        slot = (slot + 1) & mask;
+    }
+}
+
+/* host construction of exactly the layout lv_map_build.cu produces: Morton-sorted points, per level
+ * a 32-byte-slot hash table; level 0 dilated by one voxel and with halo buckets (own points first,
+ * then neighbours 0..26) */
+ShimMap* shim_map_create(const float* xyz, int64_t m, float cell, double max_dist) {
     ShimMap* sm = new ShimMap();
     const float inv = 1.0f / cell;
     std::vector<uint64_t> keys(m);
     for (int64_t i = 0; i < m; ++i)
-        keys[i] = voxel_key(voxel_coord(xyz[3 * i], inv), voxel_coord(xyz[3 * i + 1], inv), voxel_coord(xyz[3 * i + 2], inv));
+        keys[i] = morton3(voxel_coord(xyz[3 * i], inv), voxel_coord(xyz[3 * i + 1], inv), voxel_coord(xyz[3 * i + 2], inv));
     std::vector<uint32_t> order(m);
     std::iota(order.begin(), order.end(), 0u);
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
     sm->pts.resize(m);
-    int64_t heads = 0;
+    std::vector<uint64_t> ks(m);
     for (int64_t j = 0; j < m; ++j) {
         const uint32_t s = order[j];
         float4 p;
@@ -58,29 +72,73 @@ ShimMap* shim_map_create(const float* xyz, int64_t m, float cell) {
         int32_t si = (int32_t)s;
         memcpy(&p.w, &si, 4);
         sm->pts[j] = p;
-        if (j == 0 || keys[order[j - 1]] != keys[s]) ++heads;
+        ks[j] = keys[s];
     }
-    uint32_t slots = 1024;
-    while (slots < 2 * heads) slots <<= 1;
-    uint4 empty; empty.x = empty.y = 0xFFFFFFFFu; empty.z = empty.w = 0;
-    sm->table.assign(slots, empty);
-    const uint32_t mask = slots - 1;
-    for (int64_t j = 0; j < m;) {
-        const uint64_t key = keys[order[j]];
-        int64_t e = j + 1;
-        while (e < m && keys[order[e]] == key) ++e;
-        uint32_t slot = voxel_hash(key) & mask;
-        while (!((sm->table[slot].x & sm->table[slot].y) == 0xFFFFFFFFu)) slot = (slot + 1) & mask;
-        sm->table[slot].x = (uint32_t)key; sm->table[slot].y = (uint32_t)(key >> 32);
-        sm->table[slot].z = (uint32_t)j; sm->table[slot].w = (uint32_t)(e - j);
-        j = e;
-    }
+    int n_levels = 1;
+    while (n_levels < kMaxLevels && (double)cell * (double)(1 << (n_levels - 1)) < max_dist) n_levels++;
     sm->view.pts = sm->pts.data();
-    sm->view.table = sm->table.data();
-    sm->view.mask = mask;
+    sm->view.n_levels = n_levels;
     sm->view.n_points = (uint32_t)m;
-    sm->view.cell = cell;
-    sm->view.inv_cell = inv;
+    sm->view.cell0 = cell;
+    sm->view.inv_cell0 = inv;
+    for (int l = 0; l < n_levels; ++l) {
+        std::vector<uint4>& tab = sm->table[l];
+        int64_t heads = 0;
+        for (int64_t j = 0; j < m; ++j)
+            if (j == 0 || (ks[j - 1] >> (3 * l)) != (ks[j] >> (3 * l))) ++heads;
+        uint32_t slots = 1024;
+        while (slots < (l == 0 ? 10 : 2) * heads) slots <<= 1;
+        uint4 empty; empty.x = empty.y = 0xFFFFFFFFu; empty.z = empty.w = 0;
+        uint4 zero; zero.x = zero.y = zero.z = zero.w = 0;
+        tab.assign(2 * (size_t)slots, zero);
+        for (uint32_t s = 0; s < slots; ++s) tab[2 * (size_t)s] = empty;
+        const uint32_t mask = slots - 1;
+        for (int64_t j = 0; j < m;) {
+            const uint64_t key = ks[j] >> (3 * l);
+            int64_t e = j + 1;
+            while (e < m && (ks[e] >> (3 * l)) == key) ++e;
+            shim_insert(tab, mask, voxel_key_from_morton(ks[j], l), (uint32_t)j, (uint32_t)(e - j), false);
+            j = e;
+        }
+        if (l == 0) {   /* dilation: empty neighbours of occupied voxels get a slot with count 0 */
+            for (int64_t j = 0; j < m; ++j) {
+                if (j > 0 && ks[j - 1] == ks[j]) continue;
+                const int bx = (int)compact21(ks[j]), by = (int)compact21(ks[j] >> 1), bz = (int)compact21(ks[j] >> 2);
+                for (int nb = 0; nb < 27; ++nb) {
+                    const int cx = bx + nb % 3 - 1, cy = by + (nb / 3) % 3 - 1, cz = bz + nb / 9 - 1;
+                    if (nb == 13 || cx < 0 || cy < 0 || cz < 0 || cx > 0x1FFFFF || cy > 0x1FFFFF || cz > 0x1FFFFF) continue;
+                    shim_insert(tab, mask, voxel_key((uint32_t)cx, (uint32_t)cy, (uint32_t)cz), 0, 0, true);
+                }
+            }
+        }
+        VoxelLevel& L = sm->view.lv[l];
+        L.table = tab.data();
+        L.mask = mask;
+        L.cell = cell * (float)(1 << l);
+    }
+    {   /* level-0 halo buckets */
+        std::vector<uint4>& tab = sm->table[0];
+        const VoxelLevel& L = sm->view.lv[0];
+        for (uint32_t s = 0; s <= L.mask; ++s) {
+            const uint4 t = tab[2 * (size_t)s];
+            if ((t.x & t.y) == 0xFFFFFFFFu) continue;
+            const uint64_t key = ((uint64_t)t.y << 32) | t.x;
+            const int bx = (int)(key & 0x1FFFFFu), by = (int)((key >> 21) & 0x1FFFFFu), bz = (int)((key >> 42) & 0x1FFFFFu);
+            const uint32_t base = (uint32_t)sm->halo.size();
+            for (int lane = 0; lane < 27; ++lane) {
+                const int nb = lane == 0 ? 13 : (lane <= 13 ? lane - 1 : lane);
+                const int cx = bx + nb % 3 - 1, cy = by + (nb / 3) % 3 - 1, cz = bz + nb / 9 - 1;
+                uint32_t st, cn;
+                if (cx < 0 || cy < 0 || cz < 0) continue;
+                if (voxel_find(L, voxel_key((uint32_t)cx, (uint32_t)cy, (uint32_t)cz), &st, &cn) < 0) continue;
+                for (uint32_t k = 0; k < cn; ++k) sm->halo.push_back(sm->pts[st + k]);
+            }
+            tab[2 * (size_t)s + 1].x = base;
+            tab[2 * (size_t)s + 1].y = (uint32_t)sm->halo.size() - base;
+        }
+        sm->view.halo = sm->halo.data();
+    }
+    for (int l = n_levels; l < kMaxLevels; ++l) sm->view.lv[l] = sm->view.lv[0];
     return sm;
 }
 void shim_map_destroy(ShimMap* m) { delete m; }
@@ -101,12 +159,19 @@ void shim_match_all(const ShimMap* sm, const double* x, const ShimParams* p, con
     Frame fr;
     make_frame(x, &fr);
     float max_d2; double gate; int max_ring;
-    search_setup(p, sm->view.cell, &max_d2, &gate, &max_ring);
+    search_setup(p, sm->view.cell0, &max_d2, &gate, &max_ring);
     for (int64_t i = 0; i < n; ++i) {
         float g[3];
         rt_apply(fr.lidar_to_world, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], g);
         Top5 t;
-        knn5(sm->view, g[0], g[1], g[2], max_d2, max_ring, t);
+        const float4* src = sm->view.halo;                     /* the two phases of lv_measure_kernel */
+        uint32_t bs, bc;
+        const bool has_bucket = level0_probe(sm->view, g[0], g[1], g[2], &bs, &bc);
+        if (!level0_scan<GroupSerial>(sm->view, g[0], g[1], g[2], max_d2, bs, bc, has_bucket, t)) {
+            const float bound0 = t.i4 >= 0 ? t.d4 : max_d2;
+            knn5_upper<GroupSerial>(sm->view, g[0], g[1], g[2], max_d2, bound0, t);
+            src = sm->view.pts;
+        }
         float abcd[4] = {0, 0, 0, 0}, d = 0;
         double row[12] = {0}, h = 0;
         bool chosen = false;
@@ -114,7 +179,7 @@ void shim_match_all(const ShimMap* sm, const double* x, const ShimParams* p, con
         const float ds[5] = {t.d0, t.d1, t.d2, t.d3, t.d4};
         if (t.i4 >= 0 && (double)t.d4 < gate) {
             float q[5][3];
-            for (int k = 0; k < 5; ++k) { q[k][0] = sm->pts[ids[k]].x; q[k][1] = sm->pts[ids[k]].y; q[k][2] = sm->pts[ids[k]].z; }
+            for (int k = 0; k < 5; ++k) { q[k][0] = src[ids[k]].x; q[k][1] = src[ids[k]].y; q[k][2] = src[ids[k]].z; }
             chosen = plane_fit(q, p->planes_threshold, abcd);
             if (chosen) {
                 d = plane_dist(abcd, g);
@@ -127,7 +192,7 @@ void shim_match_all(const ShimMap* sm, const double* x, const ShimParams* p, con
         if (g_world) memcpy(g_world + 3 * i, g, sizeof(g));
         for (int k = 0; k < 5; ++k) {
             int32_t orig = -1;
-            if (t.i4 >= 0) memcpy(&orig, &sm->pts[ids[k]].w, 4);
+            if (t.i4 >= 0) memcpy(&orig, &src[ids[k]].w, 4);
             if (nn_idx) nn_idx[5 * i + k] = orig;
             if (nn_sqd) nn_sqd[5 * i + k] = t.i4 >= 0 ? ds[k] : INFINITY;
         }
@@ -225,3 +290,26 @@ void shim_plane_fit(const float* pts5, float thr, float* abcd, int* ok) {
 int shim_sizeof_iterlog() { return (int)sizeof(IterLog); }
 
 }  // extern "C"
+
+/* diagnostics: which queries level 0 settles */
+extern "C" void shim_query_stats(const ShimMap* sm, const double* x, const float* xyz, int64_t n, double max_dist,
+                                 int32_t* level_out, int32_t* scanned_out) {
+    Frame fr;
+    make_frame(x, &fr);
+    const double gate = max_dist * max_dist;
+    float max_d2 = (float)gate;
+    if ((double)max_d2 < gate) max_d2 = nextafterf(max_d2, INFINITY);
+    for (int64_t i = 0; i < n; ++i) {
+        float g[3];
+        rt_apply(fr.lidar_to_world, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], g);
+        Top5 t;
+        uint32_t bs, bc;
+        const bool hb = level0_probe(sm->view, g[0], g[1], g[2], &bs, &bc);
+        const bool ok = level0_scan<GroupSerial>(sm->view, g[0], g[1], g[2], max_d2, bs, bc, hb, t);
+        uint32_t s, c;
+        const int slot = voxel_find(sm->view.lv[0], voxel_key(voxel_coord(g[0], sm->view.inv_cell0), voxel_coord(g[1], sm->view.inv_cell0),
+                                                              voxel_coord(g[2], sm->view.inv_cell0)), &s, &c);
+        level_out[i] = ok ? 0 : (slot < 0 ? 2 : 1);    /* 0 settled, 1 bucket but not certified, 2 no slot */
+        scanned_out[i] = slot >= 0 ? (int)sm->view.lv[0].table[2 * (size_t)slot + 1].y : 0;
+    }
+}

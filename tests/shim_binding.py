@@ -30,7 +30,7 @@ def lib():
         subprocess.check_call(["make", "-s", "-C", _DIR])
         L = C.CDLL(os.path.join(_DIR, "liblv_cpushim.so"))
         L.shim_map_create.restype = C.c_void_p
-        L.shim_map_create.argtypes = [C.POINTER(C.c_float), C.c_int64, C.c_float]
+        L.shim_map_create.argtypes = [C.POINTER(C.c_float), C.c_int64, C.c_float, C.c_double]
         L.shim_map_destroy.argtypes = [C.c_void_p]
         assert L.shim_sizeof_iterlog() == C.sizeof(IterLog)
         _lib = L
@@ -61,10 +61,10 @@ def make_params(oprm, voxel_size=0.5):
 
 
 class ShimMap:
-    def __init__(self, xyz, cell=0.5):
+    def __init__(self, xyz, cell=0.5, max_dist=2.0):
         self.L = lib()
         xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
-        self.h = self.L.shim_map_create(_f(xyz), xyz.shape[0], C.c_float(cell))
+        self.h = self.L.shim_map_create(_f(xyz), xyz.shape[0], C.c_float(cell), C.c_double(max_dist))
 
     def __del__(self):
         try:
