@@ -154,6 +154,10 @@ lv_status lv_get_state(lv_handle h, double* x, double* P);               /* get_
 lv_status lv_init_state(lv_handle h, const float q_imu[4]);
 /* Localizator::propagate -> esekf::predict (Localizator.cpp:159-173, esekfom.hpp:279-384)    */
 lv_status lv_predict(lv_handle h, const double acc[3], const double gyro[3], double dt);
+/* the same two host-side steps on caller-owned (x, P), no handle and no GPU involved           */
+lv_status lv_init_state_host(const lv_params* p, const float q_imu[4], double* x, double* P);
+lv_status lv_predict_host(const lv_params* p, const double acc[3], const double gyro[3], double dt,
+                          double* x, double* P);
 /* Localizator::correct(points, time) (Localizator.cpp:23-27): the whole iterated update.
  * xyz_lidar: HOST buffer of n deskewed points in the LiDAR frame.  logs (capacity
  * LV_MAX_EVALS) / n_evals / x_out / P_out may be NULL.                                       */

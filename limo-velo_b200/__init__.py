@@ -95,6 +95,8 @@ def lib():
     L.lv_get_state.argtypes = [vp, dp, dp]
     L.lv_init_state.argtypes = [vp, fp]
     L.lv_predict.argtypes = [vp, dp, dp, C.c_double]
+    L.lv_init_state_host.argtypes = [C.POINTER(Params), fp, dp, dp]
+    L.lv_predict_host.argtypes = [C.POINTER(Params), dp, dp, C.c_double, dp, dp]
     L.lv_correct.argtypes = [vp, fp, i64, C.c_double, C.POINTER(IterLog), i32p, dp, dp]
     L.lv_correct_device.argtypes = [vp, vp, i64, C.c_double]
     L.lv_last_logs.argtypes = [vp, C.POINTER(IterLog), i32p]
@@ -178,6 +180,24 @@ def _logs_to_py(logs, n):
                         HTH=np.array(lg.HTH[:]).reshape(12, 12), HTh=np.array(lg.HTh[:]),
                         dx=np.array(lg.dx[:]), x_after=np.array(lg.x_after[:])))
     return out
+
+
+def init_state_host(params, q_imu=(0, 0, 0, 1)):
+    """Localizator::init_IKFoM_state on the host (no GPU needed)."""
+    x, P = np.zeros(STATE_LEN), np.zeros((DOF, DOF))
+    q = np.ascontiguousarray(q_imu, dtype=np.float32)
+    _check(lib().lv_init_state_host(C.byref(params), _f(q), _d(x), _d(P)))
+    return x, P
+
+
+def predict_host(params, x, P, acc, gyro, dt):
+    """Localizator::propagate -> esekf::predict on the host (no GPU needed)."""
+    x = np.array(x, dtype=np.float64).copy()
+    P = np.array(P, dtype=np.float64).reshape(DOF, DOF).copy()
+    acc = np.ascontiguousarray(acc, dtype=np.float64)
+    gyro = np.ascontiguousarray(gyro, dtype=np.float64)
+    _check(lib().lv_predict_host(C.byref(params), _d(acc), _d(gyro), float(dt), _d(x), _d(P)))
+    return x, P
 
 
 class Localizer:

@@ -135,3 +135,15 @@ void lvh_predict(const lv_params& prm, const double acc[3], const double gyro[3]
         }
     memcpy(P, Pn, sizeof(Pn));
 }
+
+extern "C" lv_status lv_init_state_host(const lv_params* p, const float q_imu[4], double* x, double* P) {
+    if (!p || !q_imu || !x || !P) return LV_ERR_ARG;
+    lvh_init_state(*p, q_imu, x, P);
+    return LV_OK;
+}
+extern "C" lv_status lv_predict_host(const lv_params* p, const double acc[3], const double gyro[3], double dt, double* x,
+                                     double* P) {
+    if (!p || !acc || !gyro || !x || !P) return LV_ERR_ARG;
+    lvh_predict(*p, acc, gyro, dt, x, P);
+    return LV_OK;
+}

@@ -1,0 +1,99 @@
+"""BASELINE.json sizes on the GPU: 65 536-point Velodyne-64 sweep against a 1 M-point map (configs[1]),
+plus the size-independent properties the domain offers (determinism, permutation invariance of the
+normal equations, streaming predict -> correct -> map update against the oracle)."""
+import numpy as np
+import pytest
+
+import bench
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def full(lv, O):
+    prm = lv.params_from_yaml(lv.CONFIG_DIR + "/xaloc.yaml", max_map_points=bench.MAP_POINTS + 4 * 65536,
+                              max_points=65536)
+    world, mp, sweeps, x_props, truths = bench.make_scene(lv, 0, n_sweeps=3, prm=prm)
+    x0, P0 = lv.init_state_host(prm)
+    return dict(prm=prm, world=world, map=mp, sweeps=sweeps, x_props=x_props, truths=truths, P0=P0,
+                oprm=bench.oracle_params(O, prm))
+
+
+def test_full_size_update_matches_oracle(lv, O, full):
+    loc = lv.Localizer(full["prm"])
+    loc.map_build(full["map"])
+    om = O.Map(O.KNN_REF_IKDTREE if O.ref_available() else O.KNN_KDTREE)
+    om.build(full["map"])
+    sweep, x_prop = full["sweeps"][0], full["x_props"][0]
+    loc.set_state(x_prop, full["P0"])
+    st, x, P, logs = loc.correct(sweep)
+    st_o, x_o, P_o, logs_o = om.update_iterated(x_prop, full["P0"], full["oprm"], sweep)
+    assert st == st_o == 0 and len(logs) == len(logs_o)
+    for a, b in zip(logs, logs_o):
+        assert a["n_matches"] == b["n_matches"] > 40000
+        assert np.abs(a["HTH"] - b["HTH"]).max() <= 1e-11 * np.abs(b["HTH"]).max()
+        assert np.abs(a["dx"] - b["dx"]).max() < 1e-9
+    assert np.abs(x - x_o).max() < 1e-9
+    err = np.abs(O.boxminus(x, full["truths"][0]))
+    assert err[:3].max() < 5e-3 and err[3:6].max() < 5e-4          # centimetre-level localisation
+    # per-point parity at full size
+    got = loc.match_all(x_prop, sweep)
+    ref = om.match_all(x_prop, full["oprm"], sweep)
+    inside = np.isfinite(got["nn_sqd"][:, 4])
+    assert (got["nn_sqd"][inside] == ref["nn_sqd"][inside]).all()
+    assert (got["valid"] == ref["valid"]).all() and (got["plane"] == ref["plane"]).all()
+    loc.close()
+
+
+def test_determinism_and_permutation_invariance(lv, full):
+    loc = lv.Localizer(full["prm"])
+    loc.map_build(full["map"])
+    sweep, x_prop = full["sweeps"][1], full["x_props"][1]
+    a = loc.measure_reduced(x_prop, sweep)
+    b = loc.measure_reduced(x_prop, sweep)
+    assert (a[1] == b[1]).all() and (a[2] == b[2]).all() and a[3] == b[3]       # bit-identical reruns
+    perm = np.random.default_rng(0).permutation(len(sweep))
+    c = loc.measure_reduced(x_prop, sweep[perm])
+    assert c[3] == a[3]
+    assert np.abs(c[1] - a[1]).max() <= 1e-12 * np.abs(a[1]).max()              # sums are order-insensitive
+    # splitting the sweep: the normal equations are additive over points
+    d1 = loc.measure_reduced(x_prop, sweep[:30000])
+    d2 = loc.measure_reduced(x_prop, sweep[30000:])
+    assert d1[3] + d2[3] == a[3]
+    assert np.abs(d1[1] + d2[1] - a[1]).max() <= 1e-12 * np.abs(a[1]).max()
+    loc.close()
+
+
+def test_streaming_predict_correct_map_update(lv, O, full):
+    """three sweeps of the sequence: IMU propagation, iterated update, Mapper::add with the 0.2 m rule"""
+    prm = full["prm"]
+    loc = lv.Localizer(prm)
+    loc.map_build(full["map"])
+    om = O.Map(O.KNN_KDTREE)
+    om.build(full["map"])
+    x, P = full["x_props"][0].copy(), full["P0"].copy()
+    xo, Po = x.copy(), P.copy()
+    loc.set_state(x, P)
+    for k in range(3):
+        sweep = full["sweeps"][k]
+        st, x, P, logs = loc.correct(sweep, time=0.1 * k)
+        st_o, xo, Po, logs_o = om.update_iterated(xo, Po, full["oprm"], sweep)
+        assert st == st_o == 0 and [l["n_matches"] for l in logs] == [l["n_matches"] for l in logs_o]
+        assert np.abs(x - xo).max() < 1e-8
+        assert loc.L.lv_last_time_updated(loc.h) == pytest.approx(0.1 * k)
+        g = bench.world_points(sweep, x)                           # main.cpp:101: map.add(global points, t2, true)
+        loc.map_add(g, downsample=True)
+        om.add(g, downsample=True)
+        assert abs(loc.map_size() - om.size()) <= 1e-4 * om.size()
+        for _ in range(4):                                         # Localizator::propagate_to: IMU samples to the next sweep
+            acc, gyr = np.array([0.1, 0.0, 9.8]), np.array([0.0, 0.0, 0.02])
+            loc.predict(acc, gyr, 0.025)
+            xo, Po = O.predict(xo, Po, acc, gyr, 0.025, prm.covariance_gyroscope, prm.covariance_acceleration,
+                               prm.covariance_bias_gyroscope, prm.covariance_bias_acceleration)
+        # re-anchor on the next ground truth so that the synthetic sweeps (made at the true poses) stay consistent
+        if k < 2:
+            x, P = loc.get_state()
+            x[:7] = full["x_props"][k + 1][:7]
+            xo[:7] = full["x_props"][k + 1][:7]
+            loc.set_state(x, P)
+    loc.close()
