@@ -73,7 +73,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -118,7 +118,30 @@ def oracle_params(O, prm):
                          limits=list(prm.LIMITS))
 
 
+class _StdoutToStderr:
+    """The reference's ikd-Tree announces its rebuild thread on C stdout ("Multi thread started");
+    keep this process' stdout clean for the ONE JSON line by pointing fd 1 at fd 2 meanwhile."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def cpu_leg(lv, prm, mp, sweeps, x_props, P0, budget_s, threads, max_updates=None):
+    with _StdoutToStderr():
+        out = _cpu_leg(lv, prm, mp, sweeps, x_props, P0, budget_s, threads, max_updates)
+        import gc
+        gc.collect()              # the oracle map (and the ikd-Tree's farewell message) goes here
+    return out
+
+
+def _cpu_leg(lv, prm, mp, sweeps, x_props, P0, budget_s, threads, max_updates=None):
     """Time the CPU oracle (Localizator::correct restated; kNN = the reference's own ikd-Tree when
     oracle/_ref is present) on whole updates of the same workload until `budget_s` is used."""
     O = G.load_oracle()
@@ -225,7 +248,6 @@ def run_native(args, rank, local_rank, world_size):
     t_wall = time.perf_counter() - t_wall0
     if world_size > 1:
         dist.barrier()
-    clock_info = clocks.stop()
     prof = loc.profile(reset=True)
     loc.profile_enable(False)
     step_ms = sum(a.elapsed_time(b) for a, b in evs)
@@ -246,6 +268,7 @@ def run_native(args, rank, local_rank, world_size):
         e2e_s += time.perf_counter() - t0
         e2e_pts += n * len(logs)
     pose_err = float(np.abs(G.load_oracle().boxminus(x, truths[j]))[:3].max())
+    clock_info = clocks.stop()                                      # sampled over both timed regions
 
     # ---- per-sweep map update (Mapper::add + rebuild), reported beside the headline ----
     t_add = []
@@ -336,7 +359,7 @@ def world_points(sweep, x):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")

@@ -60,16 +60,18 @@ LV_HD Mat3d hat(const Vec3d& v) {   /* mtkmath.hpp:176-183 */
     return r;
 }
 
-/* Eigen::QuaternionBase::toRotationMatrix */
+/* Eigen::QuaternionBase::toRotationMatrix.  Every product and sum is rounded separately (dmul / dadd /
+ * dsub), as the reference's x86-64 build does: the rotation matrices feed the fp64 -> fp32 casts of
+ * State.cpp:53-61 and the Jacobian rows, so a contracted FMA here would show up as 1-ulp differences. */
 LV_HD Mat3d quat_to_rot(const Quatd& q) {
-    const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
-    const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
-    const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
-    const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+    const double tx = dmul(2.0, q.x), ty = dmul(2.0, q.y), tz = dmul(2.0, q.z);
+    const double twx = dmul(tx, q.w), twy = dmul(ty, q.w), twz = dmul(tz, q.w);
+    const double txx = dmul(tx, q.x), txy = dmul(ty, q.x), txz = dmul(tz, q.x);
+    const double tyy = dmul(ty, q.y), tyz = dmul(tz, q.y), tzz = dmul(tz, q.z);
     Mat3d r;
-    r.m[0] = 1 - (tyy + tzz); r.m[1] = txy - twz;       r.m[2] = txz + twy;
-    r.m[3] = txy + twz;       r.m[4] = 1 - (txx + tzz); r.m[5] = tyz - twx;
-    r.m[6] = txz - twy;       r.m[7] = tyz + twx;       r.m[8] = 1 - (txx + tyy);
+    r.m[0] = dsub(1.0, dadd(tyy, tzz)); r.m[1] = dsub(txy, twz);            r.m[2] = dadd(txz, twy);
+    r.m[3] = dadd(txy, twz);            r.m[4] = dsub(1.0, dadd(txx, tzz)); r.m[5] = dsub(tyz, twx);
+    r.m[6] = dsub(txz, twy);            r.m[7] = dadd(tyz, twx);            r.m[8] = dsub(1.0, dadd(txx, tyy));
     return r;
 }
 LV_HD Quatd quat_mul(const Quatd& a, const Quatd& b) {

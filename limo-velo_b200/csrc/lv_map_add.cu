@@ -14,8 +14,8 @@
  *
  * Tie rule (measure zero on float data, kept for determinism): a new point beats an old one at
  * equal distance (strict '<' at :507), the later of two equal new points wins.
- * Voxel membership of OLD points uses their own floor(x / ds) instead of the half-open box test
- * of Search_by_range (:1262); the two differ only for coordinates within one ulp of a voxel face.
+ * Voxel membership of OLD points follows the half-open fp32 box test of Search_by_range (:1262), see
+ * fine_coord_old.
  */
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -32,11 +32,24 @@ LV_HD uint64_t fine_key(int ix, int iy, int iz) {   /* any injective key of the 
            (uint64_t)(uint32_t)(ix + LV_KEY_BIAS);
 }
 
-__global__ void __launch_bounds__(256) lv_add_keys_kernel(const float* __restrict__ xyz, int64_t total, float ds,
+/* Voxel of an OLD map point as Search_by_range sees it (ikd_Tree.cpp:1262): the box of voxel k is
+ * [fl(k * ds), fl(k * ds) + ds) in fp32, so a point within an ulp of a face can belong to the voxel next
+ * to floor(q / ds). */
+LV_HD int fine_coord_old(float v, float ds) {
+    int k = fine_coord(v, ds);
+    const float lo = fmul((float)k, ds);
+    if (v < lo) --k;
+    else if (!(v < fadd(lo, ds))) ++k;
+    return k;
+}
+
+__global__ void __launch_bounds__(256) lv_add_keys_kernel(const float* __restrict__ xyz, int64_t total, int64_t n_old, float ds,
                                                            uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    keys[i] = fine_key(fine_coord(xyz[3 * i], ds), fine_coord(xyz[3 * i + 1], ds), fine_coord(xyz[3 * i + 2], ds));
+    const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+    keys[i] = i < n_old ? fine_key(fine_coord_old(x, ds), fine_coord_old(y, ds), fine_coord_old(z, ds))
+                        : fine_key(fine_coord(x, ds), fine_coord(y, ds), fine_coord(z, ds));   /* ikd_Tree.cpp:493-498 */
     vals[i] = (uint32_t)i;
 }
 
@@ -124,7 +137,7 @@ int lvh_map_add_points(MapBuffers& b, const float* xyz_host, int64_t n, int down
      * uint32 arrays (keep flags, scan output) — the search structure is rebuilt right after */
     uint32_t* keep = reinterpret_cast<uint32_t*>(b.pts);
     uint32_t* pos = keep + b.cap;
-    lv_add_keys_kernel<<<blocks, 256, 0, st>>>(b.xyz, total, ds, b.keys, b.vals);
+    lv_add_keys_kernel<<<blocks, 256, 0, st>>>(b.xyz, total, n_old, ds, b.keys, b.vals);
     size_t tmp = b.sort_tmp_bytes;
     if (cub::DeviceRadixSort::SortPairs(b.sort_tmp, tmp, b.keys, b.keys_sorted, b.vals, b.vals_sorted, (int)total, 0, 63, st) != cudaSuccess)
         return LV_ERR_CUDA;

@@ -206,8 +206,7 @@ struct GroupLanes {    /* G consecutive lanes of a warp (G = 8 or 32); every lan
             float m = loc.d0;
 #pragma unroll
             for (int s = 1; s < G; s <<= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, s));
-            unsigned b = __ballot_sync(0xffffffffu, loc.d0 == m) >> gbase;
-            if (G < 32) b &= (1u << G) - 1u;
+            const unsigned b = (__ballot_sync(0xffffffffu, loc.d0 == m) >> gbase) & (0xffffffffu >> (32 - G));
             const int winner = __ffs(b) - 1;                       /* lowest lane on ties */
             od[k] = m;
             oi[k] = __shfl_sync(0xffffffffu, loc.i0, (int)gbase + winner);
