@@ -275,8 +275,7 @@ enum { kSrcHalo = 0, kSrcPts = 1 };   /* ids index halo[] (level 0) or pts[] (up
 /*
  * Level 0 in two steps so that a thread block can put ALL its probes and bucket fetches in flight
  * before anything waits on them.
- *   level0_probe   one thread per query: ONE hash probe -> the halo bucket (start, count) of the
- *                  query's home voxel, and an L2 prefetch of every 128-byte line of that bucket.
+ *   level0_probe   ONE hash probe -> the halo bucket (start, count) of the query's home voxel.
  *                  Level-0 slots exist for every occupied voxel AND for every empty voxel adjacent
  *                  to one, so a query only misses here when it is farther than one voxel from all
  *                  map points (returns false).
@@ -296,13 +295,6 @@ LV_HD bool level0_probe(const VoxelMapView& m, float gx, float gy, float gz, uin
     const uint4 b = load_slot(m.lv[0].table + 2 * (size_t)slot + 1);
     *bstart = b.x;
     *bcount = b.y;
-#if defined(__CUDA_ARCH__)
-    {   /* fire-and-forget: the scan that follows finds the bucket in L2 */
-        const char* p = reinterpret_cast<const char*>(m.halo + b.x);
-        const char* e = p + (size_t)(b.y < 192u ? b.y : 192u) * sizeof(float4);
-        for (p = (const char*)((uintptr_t)p & ~(uintptr_t)127); p < e; p += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-    }
-#endif
     return true;
 }
 

@@ -69,7 +69,13 @@ def test_determinism_and_permutation_invariance(lv, full):
 
 
 def test_streaming_predict_correct_map_update(lv, O, full):
-    """three sweeps of the sequence: IMU propagation, iterated update, Mapper::add with the 0.2 m rule"""
+    """three sweeps of the sequence: IMU propagation, iterated update, Mapper::add with the 0.2 m rule.
+
+    Two oracle chains run beside the GPU: `step` restarts every update from the GPU's own prior (x, P) and
+    must agree to 1e-7 per update on identical maps; `free` never sees the GPU's state.  The free chain's
+    prior differs from the GPU's by ~1e-8 after the first update, which moves ~0.1 % of the fp32 world points by
+    one ulp and flips a handful of hard gates (Mapper.cpp:81, Plane::is_plane); one flipped match of 58 000
+    moves the pose by ~1e-5 m, so its bar is 2e-4 m (SURVEY 8c's 1e-5 m bar is for identical priors)."""
     prm = full["prm"]
     loc = lv.Localizer(prm)
     loc.map_build(full["map"])
@@ -78,31 +84,40 @@ def test_streaming_predict_correct_map_update(lv, O, full):
     x, P = full["x_props"][0].copy(), full["P0"].copy()
     xo, Po = x.copy(), P.copy()
     loc.set_state(x, P)
+    cov = (prm.covariance_gyroscope, prm.covariance_acceleration, prm.covariance_bias_gyroscope,
+           prm.covariance_bias_acceleration)
     for k in range(3):
         sweep = full["sweeps"][k]
+        x_prior, P_prior = loc.get_state()
         st, x, P, logs = loc.correct(sweep, time=0.1 * k)
-        st_o, xo, Po, logs_o = om.update_iterated(xo, Po, full["oprm"], sweep)
-        assert st == st_o == 0 and len(logs) == len(logs_o)
-        # after the first Mapper::add the two maps may differ in a few points (exact ties of the voxel rule),
-        # so Nm may differ by a handful from then on
-        for a, b in zip(logs, logs_o):
-            assert abs(a["n_matches"] - b["n_matches"]) <= (0 if k == 0 else 1e-3 * b["n_matches"])
-        assert np.abs(x[:7] - xo[:7]).max() < (1e-7 if k == 0 else 1e-5), np.abs(x - xo)
-        assert np.abs(x - xo).max() < (1e-7 if k == 0 else 1e-3), np.abs(x - xo)
+        st_s, xs, Ps, logs_s = om.update_iterated(x_prior, P_prior, full["oprm"], sweep)       # step chain
+        st_o, xo, Po, logs_o = om.update_iterated(xo, Po, full["oprm"], sweep)                 # free chain
+        assert st == st_s == st_o == 0 and len(logs) == len(logs_s) == len(logs_o)
+        for a, b, c in zip(logs, logs_s, logs_o):
+            assert a["n_matches"] == b["n_matches"]
+            assert abs(a["n_matches"] - c["n_matches"]) <= 1e-3 * c["n_matches"]
+        assert np.abs(x - xs).max() < 1e-7, np.abs(x - xs)
+        assert np.abs(P - Ps).max() <= 1e-6 * np.abs(Ps).max()
+        assert np.abs(x[:7] - xo[:7]).max() < (1e-7 if k == 0 else 2e-4), np.abs(x - xo)
+        assert np.abs(x - xo).max() < (1e-7 if k == 0 else 2e-3), np.abs(x - xo)
         assert loc.L.lv_last_time_updated(loc.h) == pytest.approx(0.1 * k)
         g = bench.world_points(sweep, x)                           # main.cpp:101: map.add(global points, t2, true)
         loc.map_add(g, downsample=True)
         om.add(g, downsample=True)
-        assert abs(loc.map_size() - om.size()) <= 1e-4 * om.size()
+        assert loc.map_size() == om.size()
         for _ in range(4):                                         # Localizator::propagate_to: IMU samples to the next sweep
             acc, gyr = -x[23:26] + np.array([0.05, 0.0, 0.0]), np.array([0.0, 0.0, 0.01])   # at rest the accelerometer reads -grav
+            x_b, P_b = loc.get_state()
             loc.predict(acc, gyr, 0.025)
-            xo, Po = O.predict(xo, Po, acc, gyr, 0.025, prm.covariance_gyroscope, prm.covariance_acceleration,
-                               prm.covariance_bias_gyroscope, prm.covariance_bias_acceleration)
+            xo, Po = O.predict(xo, Po, acc, gyr, 0.025, *cov)
+            x_a, P_a = loc.get_state()
+            x_r, P_r = O.predict(x_b, P_b, acc, gyr, 0.025, *cov)
+            assert np.abs(x_a - x_r).max() < 1e-12 and np.abs(P_a - P_r).max() <= 1e-12 * np.abs(P_r).max()
         # re-anchor on the next ground truth so that the synthetic sweeps (made at the true poses) stay consistent
         if k < 2:
             x, P = loc.get_state()
             x[:7] = full["x_props"][k + 1][:7]
             xo[:7] = full["x_props"][k + 1][:7]
             loc.set_state(x, P)
+    assert sorted(map(tuple, loc.map_points().tolist())) == sorted(map(tuple, om.points().tolist()))
     loc.close()
