@@ -357,6 +357,7 @@ static lv_status enqueue_update(lv_context* h, const float* d_xyz, int64_t n) {
     LV_CUDA(launch_ieskf_begin(h->d_ctrl, h->stream));
     h->prof.total_launches += 1;
     MeasureArgs a = make_measure_args(h, d_xyz, n);
+    a.prep = h->d_ctrl;                                           /* ieskf_prepare rides in the fit kernel */
     const int grid = measure_grid((int)n);
     for (int e = 0; e <= h->prm.MAX_NUM_ITERS; ++e) {            /* i = -1 .. max_iter-1, esekfom.hpp:1634 */
         EventPair ep;

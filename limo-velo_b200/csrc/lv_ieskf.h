@@ -19,6 +19,13 @@
 
 namespace lv {
 
+#ifndef LV_TK
+#define LV_TK(k)            /* same, stamped by whichever thread runs the statement */
+#endif
+#ifndef LV_CK
+#define LV_CK(k)            /* phase clock of the tuning build (-DLV_STEP_TIMING), see lv_measure.cu */
+#endif
+
 enum { kN = 23, kAug = 46, kMaxEvals = 8 };
 
 struct IeskfParams {
@@ -54,6 +61,17 @@ struct UpdateCtrl {
     double P[kN * kN];        /* final covariance when done                              */
     Frame frame;              /* transforms of the current iterate for the next measure  */
     IterLog logs[kMaxEvals];
+    /* ieskf_prepare() -> ieskf_step(): the part of an evaluation that depends on the iterate only */
+    double P_j[kN * kN];      /* P_ after the J blocks (esekfom.hpp:1655-1697)           */
+    double dx_new[kN];        /* J * (x [-] x_prop)                                      */
+};
+
+/* shared-memory workspace of ieskf_prepare() */
+struct PrepWork {
+    double x[kStateLen], xp[kStateLen];
+    double P[kN * kN];
+    double dx[kN], dx_new[kN];
+    double J[3][9];
 };
 
 /* shared-memory workspace of the step */
@@ -67,11 +85,16 @@ struct IeskfWork {
     double dx[kN], dx_new[kN], dxs[kN], dnd[kN];   /* dx, J*dx, dx_ (solved), masked */
     double J[3][9];           /* J blocks: SO3@3, SO3@6 (3x3), S2@21 (2x2 in the first 4) */
     double L[kN * kN];
+    double xn[kStateLen];     /* x [+] dx_ while x is still needed                        */
+    Rt32 X, IL;               /* fp32 pose / extrinsics of xn (make_frame's two halves)   */
     double pivval;
     int64_t n_matches;
     int32_t piv;
     int32_t finish;
     int32_t abort_;
+    int32_t degen;
+    int32_t eval_idx;         /* index of this evaluation's log entry                     */
+    int32_t n_evals, t, iter; /* c->n_evals, c->t, c->iter at entry                       */
 };
 
 /* executors of the "parallel phases" below: ExecSerial (host, one thread) and ExecBlock (device) */
@@ -79,6 +102,8 @@ struct ExecSerial {
     int tid, nthreads;
     LV_HD ExecSerial() : tid(0), nthreads(1) {}
     LV_HD void sync() {}
+    LV_HD bool is_task(int) const { return true; }
+    LV_HD void solve_12x25(double* M, int32_t* s_piv, double* s_pivval);
     /* partial pivoting: row p >= k with the largest |M[p][k]| (first one on ties) */
     LV_HD void pivot(const double* M, int w, int k, int n, int32_t* s_piv, double* s_pivval) {
         int p = k;
@@ -92,13 +117,15 @@ struct ExecSerial {
     }
 };
 #if defined(__CUDACC__)
-/* One thread block runs the step.  (A single-warp variant with __syncwarp instead of block barriers
- * was measured slower, 59 us vs 45 us per evaluation: 15 k dependent fp64 / shared-memory
- * instructions issue at ~8 cycles each when one warp has nothing else to switch to.) */
+/* One thread block runs the step.  (A single-warp variant of the whole step was measured slower, 59 us vs
+ * 45 us per evaluation: 15 k dependent fp64 / shared-memory instructions issue at ~8 cycles each when one
+ * warp has nothing else to switch to.  What does pay is giving each independent serial piece its own warp
+ * and keeping the 12x25 elimination inside one warp's registers, see solve_12x25.) */
 struct ExecBlock {
     int tid, nthreads;
     __device__ __forceinline__ ExecBlock() : tid(threadIdx.x), nthreads(blockDim.x) {}
     __device__ __forceinline__ void sync() { __syncthreads(); }
+    __device__ __forceinline__ bool is_task(int k) const { return tid == 32 * k; }
     /* partial pivoting by warp 0: lane i holds row k+i (n - k <= 32), shuffle arg-max, lowest row on ties */
     __device__ __forceinline__ void pivot(const double* M, int w, int k, int n, int32_t* s_piv, double* s_pivval) {
         if (tid < 32) {
@@ -113,6 +140,52 @@ struct ExecBlock {
             }
             if (tid == 0) { *s_piv = r; *s_pivval = M[r * w + k]; }
         }
+    }
+    /* Gauss-Jordan with partial pivoting on the 12 x 25 system [A | B] of the gain, inside warp 0: lane j holds
+     * column j in 12 registers, lane k picks the pivot of step k, the multipliers M[i][k] travel by shuffle.
+     * Same pivots and the same operations on the same values as gj_solve(), so the same result; 12 barrier-free
+     * steps instead of 36 block barriers.  On return M[k][12..24] = (A^-1 B)[k]. */
+    __device__ __noinline__ void solve_12x25(double* M, int32_t*, double*) {
+        if (tid < 32) {
+            const int lane = tid;
+            const unsigned full = 0xffffffffu;
+            double col[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) col[i] = lane < 25 ? M[i * 25 + lane] : 0.0;
+            if (lane == 0) LV_TK(48);
+            /* fully unrolled over k: every register index below is static, only the swap partner p is data */
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                /* lane k: arg-max of |col[i]|, i >= k, lowest row on ties (pairwise tournament) */
+                double v[12];
+                int r[12];
+#pragma unroll
+                for (int i = k; i < 12; ++i) { v[i] = fabs(col[i]); r[i] = i; }
+#pragma unroll
+                for (int s = 1; s < 12; s *= 2)
+#pragma unroll
+                    for (int i = k; i + s < 12; i += 2 * s)
+                        if (v[i + s] > v[i]) { v[i] = v[i + s]; r[i] = r[i + s]; }
+                const int p = __shfl_sync(full, r[k], k);
+                /* swap rows k and p of this lane's column */
+                double ck = col[k];
+#pragma unroll
+                for (int i = k + 1; i < 12; ++i)
+                    if (i == p) { const double tmp = col[i]; col[i] = ck; ck = tmp; }
+                const double ipv = 1.0 / __shfl_sync(full, ck, k);
+                ck *= ipv;                               /* the scaled pivot row, this lane's column */
+                col[k] = ck;
+#pragma unroll
+                for (int i = 0; i < 12; ++i)
+                    if (i != k) col[i] -= __shfl_sync(full, col[i], k) * ck;
+            }
+            if (lane == 0) LV_TK(49);
+#pragma unroll
+            for (int i = 0; i < 12; ++i)
+                if (lane >= 12 && lane < 25) M[i * 25 + lane] = col[i];
+            if (lane == 0) LV_TK(52);
+        }
+        __syncthreads();
     }
 };
 #endif
@@ -146,29 +219,42 @@ LV_HD_NOINLINE void gj_solve(Ex& ex, double* M, int n, int w, int32_t* s_piv, do
     }
 }
 
-/* rows idx..idx+d-1 of dst (all `cols` columns) = J * the same rows of src */
+LV_HD void ExecSerial::solve_12x25(double* M, int32_t* s_piv, double* s_pivval) {
+    gj_solve(*this, M, 12, 25, s_piv, s_pivval);
+}
+
+/* The three manifold blocks of the error state: SO3 @3, SO3 @6 (3x3), S2 @21 (2x2 in J[2][0:4]) */
+LV_HD int jblock_idx(int b) { return b < 2 ? 3 + 3 * b : 21; }
+LV_HD int jblock_dim(int b) { return b < 2 ? 3 : 2; }
+
+/* for each block b: rows idx_b.. of dst (all `cols` columns) = J_b * the same rows of src.  The three row
+ * sets are disjoint, so one phase serves all blocks (esekfom.hpp:1655-1697 walks them one after another). */
 template <class Ex>
-LV_HD void apply_rows(Ex& ex, double* dst, const double* src, int idx, int d, const double* J, int cols, int stride) {
-    LV_PAR(i, cols) {
+LV_HD void apply_rows3(Ex& ex, double* dst, const double* src, const double (*J)[9], int cols, int stride) {
+    LV_PAR(it, 3 * cols) {
+        const int b = it / cols, i = it - b * cols;
+        const int idx = jblock_idx(b), d = jblock_dim(b);
         double v[3], r[3];
         for (int c = 0; c < d; ++c) v[c] = src[(idx + c) * stride + i];
         for (int a = 0; a < d; ++a) {
             double s = 0;
-            for (int c = 0; c < d; ++c) s += J[a * d + c] * v[c];
+            for (int c = 0; c < d; ++c) s += J[b][a * d + c] * v[c];
             r[a] = s;
         }
         for (int a = 0; a < d; ++a) dst[(idx + a) * stride + i] = r[a];
     }
 }
-/* columns idx..idx+d-1 of M (all `rows` rows) = the same columns * J^T */
+/* for each block b: columns idx_b.. of M (all `rows` rows) = the same columns * J_b^T */
 template <class Ex>
-LV_HD void apply_cols(Ex& ex, double* M, int idx, int d, const double* J, int rows, int stride) {
-    LV_PAR(i, rows) {
+LV_HD void apply_cols3(Ex& ex, double* M, const double (*J)[9], int rows, int stride) {
+    LV_PAR(it, 3 * rows) {
+        const int b = it / rows, i = it - b * rows;
+        const int idx = jblock_idx(b), d = jblock_dim(b);
         double v[3], r[3];
         for (int c = 0; c < d; ++c) v[c] = M[i * stride + idx + c];
         for (int a = 0; a < d; ++a) {
             double s = 0;
-            for (int c = 0; c < d; ++c) s += v[c] * J[a * d + c];
+            for (int c = 0; c < d; ++c) s += v[c] * J[b][a * d + c];
             r[a] = s;
         }
         for (int a = 0; a < d; ++a) M[i * stride + idx + a] = r[a];
@@ -292,59 +378,98 @@ LV_HD bool all_eigs_above(const double* HTH, double D) {
     return true;
 }
 
+/* J block of manifold block b for the error-state vector d (esekfom.hpp:1655-1697, 1770-1812):
+ * SO3: A(d_b)^T ; S2: Nx(grav_now) * Mx(grav_prop, d_b).  LV_HD_NOINLINE: one copy of the trig code. */
+LV_HD_NOINLINE void jblock(int b, const double* d, const double* x_now, const double* x_prop, double* J) {
+    if (b < 2) {
+        const Mat3d Jt = mat3_transpose(A_matrix(load_vec3(d + 3 + 3 * b)));
+        for (int i = 0; i < 9; ++i) J[i] = Jt.m[i];
+    } else {
+        s2_J(load_vec3(x_now + kGrav), load_vec3(x_prop + kGrav), d[21], d[22], J);
+    }
+}
+
 /*
- * One evaluation (esekfom.hpp:1647-1822).  Inputs: c->x_prop/P_prop/x, w->HTH/HTh/n_matches
- * (already reduced).  Outputs: c->x (new iterate), c->frame, c->logs[], and on exit c->P, c->done.
+ * The iterate-only part of an evaluation (esekfom.hpp:1651-1697): dx = x [-] x_prop, the J blocks,
+ * dx_new = J dx and P_ = J P_prop J^T.  Nothing here depends on the measurement, so on the device it runs in a
+ * spare block of the fit kernel, beside the measurement of the same iterate, and hands P_j / dx_new to the
+ * step through UpdateCtrl.  Independent serial pieces are "tasks": on the device each runs in its own warp
+ * (ex.is_task, tasks 0..3 need >= 128 threads), on the host one after another.
+ */
+template <class Ex>
+LV_HD_NOINLINE void ieskf_prepare(Ex& ex, UpdateCtrl* c, PrepWork* w) {
+    const int n = kN;
+    LV_PAR(i, n * n) w->P[i] = c->P_prop[i];
+    LV_PAR(i, kStateLen) { w->x[i] = c->x[i]; w->xp[i] = c->x_prop[i]; }
+    ex.sync();
+    for (int b = 0; b < 3; ++b)
+        if (ex.is_task(b)) {
+            const int idx = jblock_idx(b), d = jblock_dim(b);
+            if (b < 2) {
+                const int q = b == 0 ? kRot : kOffR;
+                store_vec3(w->dx + idx, so3_log(quat_mul(quat_conj(load_quat(w->xp + q)), load_quat(w->x + q))));
+            } else {
+                s2_boxminus(load_vec3(w->x + kGrav), load_vec3(w->xp + kGrav), w->dx + 21);
+            }
+            jblock(b, w->dx, w->x, w->xp, w->J[b]);
+            for (int a = 0; a < d; ++a) {
+                double s = 0;
+                for (int k = 0; k < d; ++k) s += w->J[b][a * d + k] * w->dx[idx + k];
+                w->dx_new[idx + a] = s;
+            }
+        }
+    if (ex.is_task(3)) {
+        const int lin[5][2] = {{0, kPos}, {9, kOffT}, {12, kVel}, {15, kBg}, {18, kBa}};
+        for (int g = 0; g < 5; ++g)
+            for (int i = 0; i < 3; ++i) {
+                const double v = w->x[lin[g][1] + i] - w->xp[lin[g][1] + i];
+                w->dx[lin[g][0] + i] = v;
+                w->dx_new[lin[g][0] + i] = v;
+            }
+    }
+    ex.sync();
+    apply_rows3(ex, w->P, w->P, w->J, n, n);
+    ex.sync();
+    apply_cols3(ex, w->P, w->J, n, n);
+    ex.sync();
+    LV_PAR(i, n * n) c->P_j[i] = w->P[i];
+    LV_PAR(i, n) c->dx_new[i] = w->dx_new[i];
+}
+
+/* global -> workspace copies of one evaluation; no barrier inside (the caller's next barrier covers them) */
+template <class Ex>
+LV_HD void ieskf_load(Ex& ex, const UpdateCtrl* c, IeskfWork* w) {
+    LV_PAR(i, kN * kN) w->P[i] = c->P_j[i];
+    LV_PAR(i, kN) w->dx_new[i] = c->dx_new[i];
+    LV_PAR(i, kStateLen) { w->x[i] = c->x[i]; w->xp[i] = c->x_prop[i]; }
+    if (ex.tid == 0) {
+        w->n_evals = c->n_evals;
+        w->eval_idx = w->n_evals < kMaxEvals ? w->n_evals : kMaxEvals - 1;
+        w->t = c->t;
+        w->iter = c->iter;
+    }
+}
+
+/*
+ * One evaluation (esekfom.hpp:1699-1822) after ieskf_prepare().  Inputs: ieskf_load() done, w->HTH/HTh/n_matches
+ * reduced, all visible (a barrier after both).  Outputs: c->x (new iterate), c->frame, c->logs[], and on exit
+ * c->P, c->done.
  */
 template <class Ex>
 LV_HD_NOINLINE void ieskf_step(Ex& ex, const IeskfParams& prm, UpdateCtrl* c, IeskfWork* w) {
     const int n = kN;
+    IterLog* lg = &c->logs[w->eval_idx];
     /* Nm < n: the reference takes esekfom.hpp:1701-1709 and then reads an uninitialised HTH
      * (SURVEY 8c quirk 4).  Here: stop, report LV_TOO_FEW_MATCHES, keep the current iterate. */
-    if (ex.tid == 0) {
-        w->abort_ = 0;
-        if (w->n_matches < n) {
-            IterLog* lg = &c->logs[c->n_evals < kMaxEvals ? c->n_evals : kMaxEvals - 1];
+    if (w->n_matches < n) {
+        if (ex.tid == 0) {
             lg->n_matches = w->n_matches;
             c->status = 2; /* LV_TOO_FEW_MATCHES */
             c->done = 1;
-            w->abort_ = 1;
         }
+        return;
     }
-    LV_PAR(i, n * n) w->P[i] = c->P_prop[i];
-    LV_PAR(i, kStateLen) { w->x[i] = c->x[i]; w->xp[i] = c->x_prop[i]; }
-    ex.sync();
-    if (w->abort_) return;
-
-    /* dx = x [-] x_prop ; J blocks (esekfom.hpp:1651-1697); three independent serial pieces */
-    if (ex.tid == 0) {
-        state_boxminus(w->x, w->xp, w->dx);
-        for (int i = 0; i < n; ++i) w->dx_new[i] = w->dx[i];
-    }
-    ex.sync();
-    LV_PAR(b, 3) {
-        if (b < 2) {
-            const int idx = 3 + 3 * b;
-            const Mat3d Jt = mat3_transpose(A_matrix(load_vec3(w->dx + idx)));
-            for (int i = 0; i < 9; ++i) w->J[b][i] = Jt.m[i];
-            const Vec3d r = mat3_apply(Jt, load_vec3(w->dx + idx));
-            store_vec3(w->dx_new + idx, r);
-        } else {
-            s2_J(load_vec3(w->x + kGrav), load_vec3(w->xp + kGrav), w->dx[21], w->dx[22], w->J[2]);
-            const double a0 = w->J[2][0] * w->dx[21] + w->J[2][1] * w->dx[22];
-            const double a1 = w->J[2][2] * w->dx[21] + w->J[2][3] * w->dx[22];
-            w->dx_new[21] = a0;
-            w->dx_new[22] = a1;
-        }
-    }
-    ex.sync();
-    for (int b = 0; b < 3; ++b) {
-        const int idx = b < 2 ? 3 + 3 * b : 21, d = b < 2 ? 3 : 2;
-        apply_rows(ex, w->P, w->P, idx, d, w->J[b], n, n);
-        ex.sync();
-        apply_cols(ex, w->P, idx, d, w->J[b], n, n);
-        ex.sync();
-    }
+    LV_CK(3);
 
     /* Gain (esekfom.hpp:1722-1729).  The reference forms P_inv = ((P/R)^-1 + E^T Q E)^-1 with two 23x23
      * inverses (Q = HTH, E = [I12 0]) and uses only P_inv[:, :12].  With S = P/R the matrix-inversion
@@ -369,7 +494,10 @@ LV_HD_NOINLINE void ieskf_step(Ex& ex, const IeskfParams& prm, UpdateCtrl* c, Ie
         w->M1[it] = v;
     }
     ex.sync();
-    gj_solve(ex, w->M1, 12, 25, &w->piv, &w->pivval);
+    LV_CK(5);
+    if (ex.is_task(1)) { LV_TK(50); w->degen = all_eigs_above(w->HTH, prm.D) ? 0 : 1; LV_TK(51); }   /* beside the solve (warp 1) */
+    ex.solve_12x25(w->M1, &w->piv, &w->pivval);
+    LV_CK(6);
     LV_PAR(it, n * 13) {
         const int i = it / 13, j = it - i * 13;
         double s = 0;
@@ -386,57 +514,82 @@ LV_HD_NOINLINE void ieskf_step(Ex& ex, const IeskfParams& prm, UpdateCtrl* c, Ie
         w->dnd[i] = w->dxs[i];
     }
     ex.sync();
+    LV_CK(7);
 
-    {   /* log the reduced measurement of this evaluation (all threads) */
-        IterLog* lgp = &c->logs[c->n_evals < kMaxEvals ? c->n_evals : kMaxEvals - 1];
-        LV_PAR(i, 144) lgp->HTH[i] = w->HTH[i];
-        LV_PAR(i, 12) lgp->HTh[i] = w->HTh[i];
+    /* x [+]= dx_ (esekfom.hpp:1747), assuming the non-degenerate case (the test of :1736-1744 ran beside the
+     * solve); the rare degenerate case redoes the update below.  Pieces of make_frame() ride along. */
+    LV_PAR(i, 144) lg->HTH[i] = w->HTH[i];
+    LV_PAR(i, 12) lg->HTh[i] = w->HTh[i];
+    LV_PAR(i, n) lg->dx[i] = w->dxs[i];
+    LV_TK(24 + (ex.tid >> 5));
+    if (ex.is_task(0)) {   /* pose: pos, rot  ->  X = (R, t) in fp32 (State.cpp:51-62), R^-1 */
+        for (int i = 0; i < 3; ++i) w->xn[kPos + i] = w->x[kPos + i] + w->dnd[i];
+        const Quatd q = quat_mul(load_quat(w->x + kRot), so3_exp(load_vec3(w->dnd + 3), 0.5));
+        store_quat(w->xn + kRot, q);
+        const Mat3d R = quat_to_rot(q), Ri = quat_to_rot(quat_conj(q));
+        for (int i = 0; i < 9; ++i) { w->X.R[i] = (float)R.m[i]; c->frame.R_inv[i] = Ri.m[i]; }
+        for (int i = 0; i < 3; ++i) w->X.t[i] = (float)w->xn[kPos + i];
     }
-    if (ex.tid == 0) {
-        IterLog* lg = &c->logs[c->n_evals < kMaxEvals ? c->n_evals : kMaxEvals - 1];
-        /* degeneracy (esekfom.hpp:1736-1744): identity unless an eigenvalue of HTH[0:6,0:6] < D */
-        lg->degenerate = 0;
-        if (!all_eigs_above(w->HTH, prm.D)) {
-            degenerate_mask(w->HTH, prm.D, w->dxs, w->dnd);
-            lg->degenerate = 1;
-        }
-        state_boxplus(w->x, w->dnd);                               /* :1747 */
+    if (ex.is_task(1)) {   /* extrinsics: offset_R_L_I, offset_T_L_I */
+        for (int i = 0; i < 3; ++i) w->xn[kOffT + i] = w->x[kOffT + i] + w->dnd[9 + i];
+        const Quatd q = quat_mul(load_quat(w->x + kOffR), so3_exp(load_vec3(w->dnd + 6), 0.5));
+        store_quat(w->xn + kOffR, q);
+        const Mat3d R = quat_to_rot(q), Ri = quat_to_rot(quat_conj(q));
+        for (int i = 0; i < 9; ++i) { w->IL.R[i] = (float)R.m[i]; c->frame.RLI_inv[i] = Ri.m[i]; }
+        for (int i = 0; i < 3; ++i) w->IL.t[i] = (float)w->xn[kOffT + i];
+    }
+    if (ex.is_task(2)) store_vec3(w->xn + kGrav, s2_boxplus(load_vec3(w->x + kGrav), w->dnd[21], w->dnd[22]));
+    if (ex.is_task(3)) {
+        for (int i = 0; i < 9; ++i) w->xn[kVel + i] = w->x[kVel + i] + w->dnd[12 + i];   /* vel, bg, ba */
         int conv = 1;                                              /* :1748-1756 uses dx_ (pre-mask) */
         for (int i = 0; i < n; ++i)
             if (fabs(w->dxs[i]) > prm.limits[i]) { conv = 0; break; }
-        if (conv) c->t += 1;                                       /* :1757 */
-        if (!c->t && c->iter == prm.max_iter - 2) conv = 1;        /* :1759-1762 */
+        const int t = w->t + conv;                                 /* :1757 */
+        if (!t && w->iter == prm.max_iter - 2) conv = 1;           /* :1759-1762 */
         lg->n_matches = w->n_matches;
         lg->converged = conv;
-        for (int i = 0; i < n; ++i) lg->dx[i] = w->dxs[i];
-        for (int i = 0; i < kStateLen; ++i) { lg->x_after[i] = w->x[i]; c->x[i] = w->x[i]; }
-        c->n_evals += 1;
-        w->finish = (c->t > 1 || c->iter == prm.max_iter - 1) ? 1 : 0;   /* :1764 */
-        c->iter += 1;
-        if (!w->finish) make_frame(w->x, &c->frame);
+        c->t = t;
+        c->n_evals = w->n_evals + 1;
+        w->finish = (t > 1 || w->iter == prm.max_iter - 1) ? 1 : 0;   /* :1764 */
+        c->iter = w->iter + 1;
+    }
+    if ((ex.tid & 31) == 0 && ex.tid < 160) LV_TK(32 + (ex.tid >> 5));
+    ex.sync();
+    if (w->degen) {        /* esekfom.hpp:1736-1744: mask dx_[0:6] and redo the boxplus serially */
+        if (ex.tid == 0) {
+            degenerate_mask(w->HTH, prm.D, w->dxs, w->dnd);
+            for (int i = 0; i < kStateLen; ++i) w->xn[i] = w->x[i];
+            state_boxplus(w->xn, w->dnd);
+            make_frame(w->xn, &c->frame);
+        }
+        ex.sync();
+    } else if (ex.tid == 0 && !w->finish) {
+        c->frame.lidar_to_world = rt_mul(w->X, w->IL);
+        c->frame.world_to_lidar = rt_mul(rt_inv(w->IL), rt_inv(w->X));
+        c->frame.lidar_to_imu = w->IL;
+    }
+    if (ex.is_task(1)) lg->degenerate = w->degen;
+    LV_PAR(i, kStateLen) {
+        const double v = w->xn[i];
+        w->x[i] = v;
+        c->x[i] = v;
+        lg->x_after[i] = v;
     }
     ex.sync();
+    LV_CK(8);
     if (!w->finish) return;
 
     /* exit block, esekfom.hpp:1766-1817 */
     LV_PAR(i, n * n) w->L[i] = w->P[i];
-    if (ex.tid == 0) {
-        for (int b = 0; b < 2; ++b) {
-            const Mat3d Jt = mat3_transpose(A_matrix(load_vec3(w->dxs + 3 + 3 * b)));
-            for (int i = 0; i < 9; ++i) w->J[b][i] = Jt.m[i];
-        }
-        s2_J(load_vec3(w->x + kGrav), load_vec3(w->xp + kGrav), w->dxs[21], w->dxs[22], w->J[2]);
-    }
+    for (int b = 0; b < 3; ++b)
+        if (ex.is_task(b)) jblock(b, w->dxs, w->x, w->xp, w->J[b]);
     ex.sync();
-    for (int b = 0; b < 3; ++b) {
-        const int idx = b < 2 ? 3 + 3 * b : 21, d = b < 2 ? 3 : 2;
-        apply_rows(ex, w->L, w->P, idx, d, w->J[b], n, n);
-        apply_rows(ex, w->Kx, w->Kx, idx, d, w->J[b], 12, 12);
-        ex.sync();
-        apply_cols(ex, w->L, idx, d, w->J[b], n, n);
-        apply_cols(ex, w->P, idx, d, w->J[b], n, n);
-        ex.sync();
-    }
+    apply_rows3(ex, w->L, w->P, w->J, n, n);
+    apply_rows3(ex, w->Kx, w->Kx, w->J, 12, 12);
+    ex.sync();
+    apply_cols3(ex, w->L, w->J, n, n);
+    apply_cols3(ex, w->P, w->J, n, n);
+    ex.sync();
     LV_PAR(it, n * n) {                                            /* :1817 */
         const int i = it / n, j = it - i * n;
         double s = 0;
@@ -445,6 +598,7 @@ LV_HD_NOINLINE void ieskf_step(Ex& ex, const IeskfParams& prm, UpdateCtrl* c, Ie
     }
     if (ex.tid == 0) c->done = 1;
     ex.sync();
+    LV_CK(9);
 }
 
 /* start of an update: x_prop = x, P_prop = P, loop counters (esekfom.hpp:1622-1634) */

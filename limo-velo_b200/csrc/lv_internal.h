@@ -12,7 +12,7 @@
 
 namespace lv {
 
-enum { kMeasureThreads = 128, kPartialStride = 96, kStepThreads = 256 };
+enum { kMeasureThreads = 128, kPartialStride = 96, kStepThreads = 512 };
 
 /* per-launch constants of the fused measure kernel */
 struct MeasureArgs {
@@ -21,6 +21,7 @@ struct MeasureArgs {
     int32_t n_tiles;           /* ceil(n / kMeasureThreads)                               */
     VoxelMapView map;
     const UpdateCtrl* ctrl;    /* frame + done flag                                       */
+    UpdateCtrl* prep;          /* non-NULL: block 0 of the fit kernel runs ieskf_prepare() */
     float max_d2;              /* smallest float >= MAX_DIST_PLANE^2 (search radius^2)    */
     double gate_d2;            /* MAX_DIST_PLANE^2 in double (Plane.cpp:42)               */
     int32_t max_ring;

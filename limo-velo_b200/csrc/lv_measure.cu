@@ -20,6 +20,14 @@
  */
 #include <stdlib.h>
 
+#ifdef LV_STEP_TIMING   /* tuning build only: per-phase clocks of the step kernel */
+__device__ long long g_step_clk[64];
+#ifdef __CUDA_ARCH__
+#define LV_CK(k) do { if (threadIdx.x == 0) g_step_clk[k] = clock64(); } while (0)
+#define LV_TK(k) do { g_step_clk[k] = clock64(); } while (0)
+#endif
+#endif
+
 #include "lv_internal.h"
 
 namespace lv {
@@ -120,8 +128,23 @@ __global__ void __launch_bounds__(128) lv_search_upper_kernel(const MeasureArgs 
  *   reduce      the 90 unique sums of H^T H and H^T h over the tile, fixed order; H (Nm x 12 fp64) is
  *               never materialised
  */
-__global__ void __launch_bounds__(kMeasureThreads) lv_fit_kernel(const MeasureArgs a) {
+/* ieskf_prepare() of the iterate being measured, in one spare block (see lv_ieskf.h) */
+__device__ __noinline__ void prepare_block(UpdateCtrl* c) {
+    __shared__ PrepWork s_prep;
+    ExecBlock ex;
+    ieskf_prepare(ex, c, &s_prep);
+}
+
+__global__ void __launch_bounds__(kMeasureThreads, 4) lv_fit_kernel(const MeasureArgs a) {
     if (a.ctrl->done) return;
+    /* with a.prep the grid has one extra block in front; it is dispatched first and is done long before
+     * the measurement blocks, so the iterate-only algebra costs the update no time of its own */
+    const int n_blocks = a.prep ? (int)gridDim.x - 1 : (int)gridDim.x;
+    const int bid = a.prep ? (int)blockIdx.x - 1 : (int)blockIdx.x;
+    if (bid < 0) {
+        prepare_block(a.prep);
+        return;
+    }
 
     __shared__ Frame s_frame;
     __shared__ double s_rows[13 * LV_ROW_STRIDE];
@@ -137,7 +160,7 @@ __global__ void __launch_bounds__(kMeasureThreads) lv_fit_kernel(const MeasureAr
     double acc = 0.0;
     int count = 0;
 
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    for (int tile = bid; tile < a.n_tiles; tile += n_blocks) {
         const int i = tile * kMeasureThreads + tid;
         bool chosen = false;
         double row[12], hval = 0.0;
@@ -214,38 +237,32 @@ __global__ void __launch_bounds__(kMeasureThreads) lv_fit_kernel(const MeasureAr
         }
         __syncthreads();
     }
-    double* out = a.partials + (size_t)blockIdx.x * kPartialStride;
+    double* out = a.partials + (size_t)bid * kPartialStride;
     if (tid < 90) out[tid] = acc;
     if (tid == 90) out[90] = (double)count;
 }
 
 /* ---- fixed-order reduction of the per-block partials ---------------------------------------- */
-/* Each of the 16 warps of the block owns blocks w, w+16, ...; lanes own elements lane, lane+32,
- * lane+64.  Then the 16 warp sums are added in warp order.  Deterministic for a given grid.    */
-__device__ void reduce_partials_block(const double* partials, int n_partials, double* s_tmp /*16*96*/,
+/* Warp w of the block owns rows w, w + nwarps, ...; lanes own elements lane, lane+32, lane+64.  Rows are
+ * fetched 8 at a time (24 independent loads per lane) and
+ * added in row order; then the warp sums are added in warp order.  Deterministic for a given grid. */
+__device__ void reduce_partials_block(const double* partials, int n_partials, double* s_tmp /*nwarps*96*/,
                                       double* HTH, double* HTh, int64_t* nm) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     double a0 = 0, a1 = 0, a2 = 0;
-    int b = warp;
-    for (; b + 3 * nwarps < n_partials; b += 4 * nwarps) {   /* 12 independent loads in flight, fixed order of adds */
-        const double* p0 = partials + (size_t)b * kPartialStride;
-        const double* p1 = p0 + (size_t)nwarps * kPartialStride;
-        const double* p2 = p1 + (size_t)nwarps * kPartialStride;
-        const double* p3 = p2 + (size_t)nwarps * kPartialStride;
-        const double x0 = p0[lane], y0 = p0[lane + 32], z0 = p0[lane + 64];
-        const double x1 = p1[lane], y1 = p1[lane + 32], z1 = p1[lane + 64];
-        const double x2 = p2[lane], y2 = p2[lane + 32], z2 = p2[lane + 64];
-        const double x3 = p3[lane], y3 = p3[lane + 32], z3 = p3[lane + 64];
-        a0 += x0; a1 += y0; a2 += z0;
-        a0 += x1; a1 += y1; a2 += z1;
-        a0 += x2; a1 += y2; a2 += z2;
-        a0 += x3; a1 += y3; a2 += z3;
-    }
-    for (; b < n_partials; b += nwarps) {
-        const double* p = partials + (size_t)b * kPartialStride;
-        a0 += p[lane];
-        a1 += p[lane + 32];
-        a2 += p[lane + 64];
+    for (int b = warp; b < n_partials; b += 8 * nwarps) {
+        double v[8][3];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int row = b + r * nwarps;
+            const double* p = partials + (size_t)row * kPartialStride;
+            const bool in = row < n_partials;
+            v[r][0] = in ? p[lane] : 0.0;
+            v[r][1] = in ? p[lane + 32] : 0.0;
+            v[r][2] = in ? p[lane + 64] : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) { a0 += v[r][0]; a1 += v[r][1]; a2 += v[r][2]; }
     }
     s_tmp[warp * 96 + lane] = a0;
     s_tmp[warp * 96 + lane + 32] = a1;
@@ -273,8 +290,32 @@ __global__ void __launch_bounds__(kStepThreads) lv_ieskf_step_kernel(UpdateCtrl*
     if (c->done) return;
     __shared__ IeskfWork w;
     __shared__ double s_tmp[(kStepThreads / 32) * 96];
-    reduce_partials_block(partials, n_partials, s_tmp, w.HTH, w.HTh, &w.n_matches);
     ExecBlock ex;
+    LV_CK(0);
+    /* ieskf_load(), split: the loads are issued here and parked in shared memory after the reduction, so
+     * they are in flight together with the partials */
+    static_assert(kStepThreads >= 75 && 2 * kStepThreads >= kN * kN, "one pass for the state, two for P_j");
+    const int t = threadIdx.x;
+    const double pj0 = t < kN * kN ? c->P_j[t] : 0.0;
+    const double pj1 = t + kStepThreads < kN * kN ? c->P_j[t + kStepThreads] : 0.0;
+    double sv = 0.0;
+    if (t < 26) sv = c->x[t];
+    else if (t < 52) sv = c->x_prop[t - 26];
+    else if (t < 75) sv = c->dx_new[t - 52];
+    int cv = 0;
+    if (t >= 96 && t < 99) cv = t == 96 ? c->n_evals : (t == 97 ? c->t : c->iter);
+    LV_CK(1);
+    reduce_partials_block(partials, n_partials, s_tmp, w.HTH, w.HTh, &w.n_matches);
+    if (t < kN * kN) w.P[t] = pj0;
+    if (t + kStepThreads < kN * kN) w.P[t + kStepThreads] = pj1;
+    if (t < 26) w.x[t] = sv;
+    else if (t < 52) w.xp[t - 26] = sv;
+    else if (t < 75) w.dx_new[t - 52] = sv;
+    if (t == 96) { w.n_evals = cv; w.eval_idx = cv < kMaxEvals ? cv : kMaxEvals - 1; }
+    if (t == 97) w.t = cv;
+    if (t == 98) w.iter = cv;
+    __syncthreads();
+    LV_CK(2);
     ieskf_step(ex, prm, c, &w);
 }
 
@@ -332,7 +373,7 @@ cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st) {
         default: lv_search_kernel<4><<<sgrid, LV_SEARCH_THREADS, 0, st>>>(a); break;
     }
     lv_search_upper_kernel<<<148 * 2, 128, 0, st>>>(a);
-    lv_fit_kernel<<<grid, kMeasureThreads, 0, st>>>(a);
+    lv_fit_kernel<<<grid + (a.prep ? 1 : 0), kMeasureThreads, 0, st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_ieskf_begin(UpdateCtrl* c, cudaStream_t st) {
@@ -360,3 +401,9 @@ cudaError_t launch_l2_flush(void* buf, size_t bytes, cudaStream_t st) {
 }
 
 }  // namespace lv
+
+#ifdef LV_STEP_TIMING
+extern "C" int lv_debug_step_clocks(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, g_step_clk, sizeof(long long) * 64);
+}
+#endif

@@ -233,12 +233,15 @@ int shim_update(const ShimMap* sm, double* x, double* P, const ShimParams* p, co
     prm.R = p->R; prm.D = p->D; prm.max_iter = p->max_iter; prm.estimate_extrinsics = p->estimate_extrinsics;
     for (int i = 0; i < kN; ++i) prm.limits[i] = p->limits[i];
     ExecSerial ex;
+    PrepWork* pw = new PrepWork();
     ieskf_begin(ex, c);
     std::vector<double> rows(13 * n);
     std::vector<uint8_t> valid(n);
     for (int e = 0; e <= p->max_iter && !c->done; ++e) {
         shim_match_all(sm, c->x, p, xyz, n, valid.data(), nullptr, nullptr, nullptr, nullptr, nullptr, rows.data());
         reduce_rows(rows.data(), valid.data(), n, w->HTH, w->HTh, &w->n_matches);
+        ieskf_prepare(ex, c, pw);
+        ieskf_load(ex, c, w);
         ieskf_step(ex, prm, c, w);
     }
     memcpy(x, c->x, sizeof(double) * kStateLen);
@@ -248,6 +251,7 @@ int shim_update(const ShimMap* sm, double* x, double* P, const ShimParams* p, co
     const int st = c->status;
     delete c;
     delete w;
+    delete pw;
     return st;
 }
 
@@ -269,6 +273,10 @@ int shim_step(const double* x_prop, const double* P_prop, const double* x_cur, c
     memcpy(w->HTh, HTh, sizeof(double) * 12);
     w->n_matches = nm;
     ExecSerial ex;
+    PrepWork* pw = new PrepWork();
+    ieskf_prepare(ex, c, pw);
+    delete pw;
+    ieskf_load(ex, c, w);
     ieskf_step(ex, prm, c, w);
     memcpy(dx_out, c->logs[0].dx, sizeof(double) * kN);
     memcpy(x_new, c->x, sizeof(double) * kStateLen);
