@@ -84,10 +84,18 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def wait_first(self, timeout=3.0):
+        """block until nvidia-smi delivers its first row (its start-up takes ~0.1 s), then mark the window start"""
+        t0 = time.perf_counter()
+        while self.proc and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.005)
+        self.first = len(self.rows)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        self.rows = self.rows[getattr(self, "first", 0):]
+        time.sleep(0.03)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -227,15 +235,15 @@ def run_native(args, rank, local_rank, world_size):
         loc.flush_l2()
         return e0, e1, logs
 
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     for i in range(args.warmup):
         step_device(i)
     torch.cuda.synchronize()
+    clocks.wait_first()                                             # rows from here on fall inside the timed regions
     if world_size > 1:
         dist.barrier()
-    loc.profile_enable(True)
     loc.profile(reset=True)
-    clocks = ClockSampler(local_rank)
-    clocks.start()
     torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
     evs, evals, matched = [], 0, 0
@@ -248,10 +256,21 @@ def run_native(args, rank, local_rank, world_size):
     t_wall = time.perf_counter() - t_wall0
     if world_size > 1:
         dist.barrier()
-    prof = loc.profile(reset=True)
-    loc.profile_enable(False)
+    launches = loc.profile(reset=True)["total_launches"]
     step_ms = sum(a.elapsed_time(b) for a, b in evs)
     pts = n * evals
+
+    # ---- per-kernel device time (roofline): the same steps again with CUDA events around each kernel group.
+    # The timed region above replays an update as ONE CUDA graph; events between its kernels would add bubbles,
+    # so the per-kernel numbers come from this separate pass of direct launches on the same stream. ----
+    loc.profile_enable(True)
+    loc.profile(reset=True)
+    prof_steps = min(args.steps, 50)
+    for i in range(prof_steps):
+        step_device(args.warmup + i)
+    torch.cuda.synchronize()
+    prof = loc.profile(reset=True)
+    loc.profile_enable(False)
 
     # ---- e2e: the public host-buffer call, pinned H2D + kernels + D2H of the result, wall clock ----
     for i in range(min(3, args.warmup)):
@@ -281,7 +300,7 @@ def run_native(args, rank, local_rank, world_size):
         t_add.append(time.perf_counter() - t0)
 
     # ---- max over ranks / totals ----
-    tot = torch.tensor([step_ms, float(pts), float(matched), e2e_s, float(e2e_pts), float(prof["total_launches"])],
+    tot = torch.tensor([step_ms, float(pts), float(matched), e2e_s, float(e2e_pts), float(launches)],
                        dtype=torch.float64, device="cuda")
     if world_size > 1:
         mx = tot.clone()
@@ -292,7 +311,7 @@ def run_native(args, rank, local_rank, world_size):
         pts_all, matched_all, e2e_pts_all, launches_all = float(sm[1]), float(sm[2]), float(sm[4]), float(sm[5])
     else:
         step_ms_max, e2e_s_max = step_ms, e2e_s
-        pts_all, matched_all, e2e_pts_all, launches_all = float(pts), float(matched), float(e2e_pts), float(prof["total_launches"])
+        pts_all, matched_all, e2e_pts_all, launches_all = float(pts), float(matched), float(e2e_pts), float(launches)
 
     if rank == 0:
         peaks = {}
@@ -304,17 +323,21 @@ def run_native(args, rank, local_rank, world_size):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         m_launches = max(1, prof["measure_launches"])
         m_ms = prof["measure_ms"] / m_launches
-        achieved = ALGO_BYTES_PER_POINT * n / (m_ms * 1e-3) / 1e9 if m_ms > 0 else 0.0
+        k_ms = {"lv_search_kernel": prof["search_ms"] / m_launches, "lv_search_upper_kernel": prof["search_upper_ms"] / m_launches,
+                "lv_fit_kernel": prof["fit_ms"] / m_launches, "lv_ieskf_step_kernel": prof["solve_ms"] / max(1, prof["solve_launches"])}
+        dominant = max(k_ms, key=k_ms.get)                          # by device time per evaluation
+        achieved = ALGO_BYTES_PER_POINT * n / (k_ms[dominant] * 1e-3) / 1e9 if k_ms[dominant] > 0 else 0.0
         traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "measure_kernel_traffic.json")))["dram_bytes_per_launch"]
+        try:                                                        # dram bytes per launch from the committed ncu --set full capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))
+            traffic = next(v["dram_bytes_per_launch"] for k, v in tr.items() if k.startswith(dominant))
         except Exception:
             pass
         cpu = None
         if not args.no_cpu:
             O = G.load_oracle()
             cpu, _, _, _ = cpu_leg(lv, prm, mp, sweeps, x_props, P0, args.cpu_seconds, 1)
-        sz_ctrl = 8 * (26 + 529) * 2 + 32 + 8 * (8 + 8 + 8 * (144 + 12 + 23 + 26)) + 400
+        sz_ctrl = loc.result_bytes()
         line = {
             "metric": METRIC, "value": pts_all / (step_ms_max * 1e-3), "unit": UNIT, "n_gpus": world_size,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms_max / args.steps,
@@ -327,13 +350,16 @@ def run_native(args, rank, local_rank, world_size):
                     "d2h_bytes_per_step": sz_ctrl, "ms_per_step": 1e3 * e2e_s_max / args.steps,
                     "how": "lv_correct() on a pinned host sweep, wall clock around the blocking call"},
             "gpu_launches": int(round(launches_all)) - args.steps * world_size,   # minus the L2-flush kernels
-            "kernel_ms": {"measure_avg": m_ms, "measure_launches": prof["measure_launches"],
+            "kernel_ms": {"how": "separate pass of %d steps, direct launches, CUDA events around each kernel group; "
+                                 "the timed region replays each update as one CUDA graph" % prof_steps,
+                          "per_evaluation": k_ms,
+                          "measure_avg": m_ms, "measure_launches": prof["measure_launches"],
                           "idle_measure_launches": prof.get("idle_launches", 0),
                           "solve_avg": prof["solve_ms"] / max(1, prof["solve_launches"]),
                           "solve_launches": prof["solve_launches"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                          "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "lv_measure_kernel", "algorithmic_bytes_per_launch": ALGO_BYTES_PER_POINT * n},
+                         "kernel": dominant, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_POINT * n},
             "cpu_baseline": cpu,
             "map_update": {"lv_map_add_ms": 1e3 * min(t_add), "points_added": n, "map_points": loc.map_size()},
             "final_position_error_m": pose_err,
@@ -359,7 +385,7 @@ def world_points(sweep, x):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")

@@ -96,13 +96,17 @@ typedef struct lv_iter_log {
 } lv_iter_log;
 
 typedef struct lv_profile {
-    double measure_ms;        /* sum of device time of the fused measure kernel            */
+    double measure_ms;        /* sum of device time of the measurement kernels (search + fit) */
     double solve_ms;          /* sum of device time of the IESKF step kernel               */
     double build_ms;          /* sum of device time of map (re)builds                      */
     int64_t measure_launches, solve_launches, build_launches;
     int64_t total_launches;   /* every kernel launched by this handle since the last reset */
     double idle_ms;           /* launches that found the update already finished (early exit) */
     int64_t idle_launches;
+    /* measure_ms split by kernel (each launched once per h-evaluation) */
+    double search_ms;         /* lv_search_kernel: exact 5-NN at level 0                   */
+    double search_upper_ms;   /* lv_search_upper_kernel: the queries level 0 cannot certify */
+    double fit_ms;            /* lv_fit_kernel: plane fit, Jacobian rows, normal equations  */
 } lv_profile;
 
 /* ------------------------------------------------------------------------------------------ */
@@ -116,6 +120,8 @@ lv_status lv_create(const lv_params* p, lv_handle* out);
 void lv_destroy(lv_handle h);
 const char* lv_last_error(void);
 const char* lv_version(void);
+/* bytes one lv_correct() reads back from the device (state, covariance, logs): the D2H side of its e2e cost */
+int64_t lv_result_bytes(void);
 
 /* ---- Mapper boundary (include/Headers/Mapper.hpp:17-23) ---------------------------------- */
 /* Mapper::add on an empty map == KD_TREE::Build, no downsampling (Mapper.cpp:26,68-71).      */

@@ -48,7 +48,8 @@ class IterLog(C.Structure):
 class Profile(C.Structure):
     _fields_ = [("measure_ms", C.c_double), ("solve_ms", C.c_double), ("build_ms", C.c_double),
                 ("measure_launches", C.c_int64), ("solve_launches", C.c_int64), ("build_launches", C.c_int64),
-                ("total_launches", C.c_int64), ("idle_ms", C.c_double), ("idle_launches", C.c_int64)]
+                ("total_launches", C.c_int64), ("idle_ms", C.c_double), ("idle_launches", C.c_int64),
+                ("search_ms", C.c_double), ("search_upper_ms", C.c_double), ("fit_ms", C.c_double)]
 
 
 def build(verbose=False):
@@ -80,6 +81,7 @@ def lib():
     L.lv_destroy.restype = None
     L.lv_last_error.restype = C.c_char_p
     L.lv_version.restype = C.c_char_p
+    L.lv_result_bytes.restype = C.c_int64
     L.lv_map_build.argtypes = [vp, fp, i64]
     L.lv_map_add.argtypes = [vp, fp, i64, C.c_int]
     L.lv_map_size.argtypes = [vp]
@@ -304,6 +306,9 @@ class Localizer:
 
     def correct_device(self, d_ptr, n, time=0.0):
         return _check(self.L.lv_correct_device(self.h, d_ptr, n, float(time)), allow=(EMPTY_MAP,))
+
+    def result_bytes(self):
+        return int(self.L.lv_result_bytes())
 
     def last_logs(self):
         logs = (IterLog * MAX_EVALS)()

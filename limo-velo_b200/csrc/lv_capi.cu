@@ -39,7 +39,7 @@ static void set_error(const std::string& s) { g_last_error = s; }
         }                                                                                        \
     } while (0)
 
-struct EventPair { cudaEvent_t a, b; int kind; int upd; int slot; };   /* kind 0 measure, 1 solve, 2 build */
+struct EventPair { cudaEvent_t a, b; int kind; int upd; int slot; };   /* kind 0 measure, 1 solve, 2 build, 3 search, 4 search-upper, 5 fit */
 enum { kNevalsRing = 4096 };
 
 struct lv_context {
@@ -77,6 +77,20 @@ struct lv_context {
     int32_t* h_nevals = nullptr;       /* pinned ring: n_evals of profiled updates */
     uint32_t update_seq = 0;
     IeskfParams iprm;
+    /* one update = begin + (MAX_NUM_ITERS + 1) x (search, search-upper, fit, step): replayed as a CUDA graph
+     * (one per sweep-capacity bucket) so that the host pays one launch instead of ~21 */
+    struct UpdateGraph {
+        int64_t cap;
+        cudaGraph_t graph;
+        cudaGraphExec_t exec;
+        cudaGraphNode_t begin_node;
+        std::vector<cudaGraphNode_t> measure_nodes[3];   /* search, search-upper, fit: they carry the map view */
+        uint64_t map_version;
+    };
+    std::vector<UpdateGraph> graphs;
+    MeasureJob* d_job = nullptr;
+    bool use_graph = true;
+    uint64_t map_version = 0;          /* bumped by every rebuild: captured map views go stale */
 };
 
 static lv_status drain_events(lv_context* h) {
@@ -89,6 +103,9 @@ static lv_status drain_events(lv_context* h) {
         const bool idle = e.upd >= 0 && e.slot >= h->h_nevals[e.upd % kNevalsRing];
         if (idle) { h->prof.idle_ms += ms; h->prof.idle_launches++; }
         else if (e.kind == 0) { h->prof.measure_ms += ms; h->prof.measure_launches++; }
+        else if (e.kind == 3) { h->prof.search_ms += ms; h->prof.measure_ms += ms; h->prof.measure_launches++; }
+        else if (e.kind == 4) { h->prof.search_upper_ms += ms; h->prof.measure_ms += ms; }
+        else if (e.kind == 5) { h->prof.fit_ms += ms; h->prof.measure_ms += ms; }
         else if (e.kind == 1) { h->prof.solve_ms += ms; h->prof.solve_launches++; }
         else { h->prof.build_ms += ms; h->prof.build_launches++; }
         h->pool.push_back(e);
@@ -159,6 +176,7 @@ extern "C" {
 
 const char* lv_last_error(void) { return g_last_error.c_str(); }
 const char* lv_version(void) { return "limovelo_b200 0.1 (sm_100a)"; }
+int64_t lv_result_bytes(void) { return (int64_t)sizeof(UpdateCtrl); }
 
 lv_status lv_create(const lv_params* p, lv_handle* out) {
     if (!p || !out) return LV_ERR_ARG;
@@ -207,6 +225,9 @@ lv_status lv_create(const lv_params* p, lv_handle* out) {
     LV_CUDA(cudaMalloc(&h->d_nn_a, sizeof(int4) * p->max_points));
     LV_CUDA(cudaMalloc(&h->d_nn_b, sizeof(int2) * p->max_points));
     LV_CUDA(cudaMalloc(&h->d_hard_list, sizeof(uint32_t) * (p->max_points + 1)));
+    LV_CUDA(cudaMalloc(&h->d_job, sizeof(MeasureJob)));
+    measure_init();
+    h->use_graph = getenv("LV_NO_GRAPH") == nullptr;
     LV_CUDA(cudaMalloc(&h->d_ctrl, sizeof(UpdateCtrl)));
     LV_CUDA(cudaMemset(h->d_ctrl, 0, sizeof(UpdateCtrl)));
     LV_CUDA(cudaMallocHost(&h->h_ctrl, sizeof(UpdateCtrl)));
@@ -229,6 +250,8 @@ void lv_destroy(lv_handle h) {
     cudaStreamSynchronize(h->stream);
     for (auto& e : h->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : h->pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (auto& u : h->graphs) { cudaGraphExecDestroy(u.exec); cudaGraphDestroy(u.graph); }
+    cudaFree(h->d_job);
     MapBuffers& m = h->map;
     cudaFree(m.xyz); cudaFree(m.xyz_alt); cudaFree(m.keys); cudaFree(m.keys_sorted); cudaFree(m.vals); cudaFree(m.vals_sorted);
     cudaFree(m.pts);
@@ -249,6 +272,7 @@ static lv_status rebuild(lv_context* h) {
     const bool pr = prof_begin(h, 2, &ep);
     int launches = 0;
     LV_CUDA(map_rebuild(h->map, h->stream, &launches));
+    h->map_version++;
     if (pr) prof_end(h, &ep);
     h->prof.total_launches += launches;
     return LV_OK;
@@ -348,28 +372,140 @@ static lv_status upload_state(lv_context* h, const double* x, const double* P) {
 }
 
 /* ---- the update ------------------------------------------------------------------------------ */
+static MeasureArgs update_measure_args(lv_context* h, const float* d_xyz, int64_t n, bool as_job) {
+    MeasureArgs a = make_measure_args(h, d_xyz, n);
+    a.prep = h->d_ctrl;                                           /* ieskf_prepare rides in the fit kernel */
+    if (as_job) a.job = h->d_job;
+    return a;
+}
+
+/* enqueue begin + all evaluations on h->stream; with `job` the sweep comes from device memory (graph capture) */
+static lv_status enqueue_update_kernels(lv_context* h, const float* d_xyz, int64_t n, bool as_job);
+
+static lv_status build_update_graph(lv_context* h, int64_t cap, lv_context::UpdateGraph* out) {
+    cudaGraph_t graph = nullptr;
+    LV_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    lv_status s = enqueue_update_kernels(h, nullptr, cap, true);
+    cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+    if (s != LV_OK || e != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return LV_ERR_CUDA; }
+        return s;
+    }
+    out->cap = cap;
+    out->graph = graph;                 /* kept: the node handles below belong to it */
+    out->map_version = h->map_version;
+    LV_CUDA(cudaGraphInstantiate(&out->exec, graph, 0));
+    /* nodes patched per launch: the begin kernel (sweep pointer and size) and, after a map update, the
+     * measurement kernels (their arguments embed the map view) */
+    MeasureArgs a = update_measure_args(h, nullptr, cap, true);
+    MeasureKernelShape shape[3];
+    measure_kernel_shapes(a, measure_grid((int)cap), shape);
+    size_t n_nodes = 0;
+    LV_CUDA(cudaGraphGetNodes(graph, nullptr, &n_nodes));
+    std::vector<cudaGraphNode_t> nodes(n_nodes);
+    LV_CUDA(cudaGraphGetNodes(graph, nodes.data(), &n_nodes));
+    out->begin_node = nullptr;
+    for (cudaGraphNode_t nd : nodes) {
+        cudaGraphNodeType t;
+        LV_CUDA(cudaGraphNodeGetType(nd, &t));
+        if (t != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams kp;
+        LV_CUDA(cudaGraphKernelNodeGetParams(nd, &kp));
+        if (kp.func == ieskf_begin_kernel_ptr()) out->begin_node = nd;
+        for (int k = 0; k < 3; ++k)
+            if (kp.func == shape[k].func) out->measure_nodes[k].push_back(nd);
+    }
+    const size_t evals = (size_t)h->prm.MAX_NUM_ITERS + 1;
+    if (!out->begin_node || out->measure_nodes[0].size() != evals || out->measure_nodes[1].size() != evals ||
+        out->measure_nodes[2].size() != evals) {
+        set_error("update graph: unexpected node set");
+        return LV_ERR_CUDA;
+    }
+    return LV_OK;
+}
+
 static lv_status enqueue_update(lv_context* h, const float* d_xyz, int64_t n) {
     if (h->state_dirty) {
         lv_status s = upload_state(h, h->x, h->P);
         if (s != LV_OK) return s;
         h->state_dirty = false;
     }
-    LV_CUDA(launch_ieskf_begin(h->d_ctrl, h->stream));
-    h->prof.total_launches += 1;
-    MeasureArgs a = make_measure_args(h, d_xyz, n);
-    a.prep = h->d_ctrl;                                           /* ieskf_prepare rides in the fit kernel */
+    if (h->profile || !h->use_graph) return enqueue_update_kernels(h, d_xyz, n, false);
+    int64_t cap = 4096;
+    while (cap < n) cap <<= 1;
+    if (cap > h->prm.max_points) cap = h->prm.max_points;
+    lv_context::UpdateGraph* g = nullptr;
+    for (auto& u : h->graphs) if (u.cap == cap) g = &u;
+    if (!g) {
+        lv_context::UpdateGraph u;
+        lv_status s = build_update_graph(h, cap, &u);
+        if (s != LV_OK) return s;
+        h->graphs.push_back(u);
+        g = &h->graphs.back();
+    }
+    UpdateCtrl* c = h->d_ctrl;
+    MeasureJob* job = h->d_job;
+    int n32 = (int)n;
+    void* args[4] = {&c, &job, &d_xyz, &n32};
+    cudaKernelNodeParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.func = const_cast<void*>(ieskf_begin_kernel_ptr());
+    kp.gridDim = dim3(1, 1, 1);
+    kp.blockDim = dim3(256, 1, 1);
+    kp.kernelParams = args;
+    LV_CUDA(cudaGraphExecKernelNodeSetParams(g->exec, g->begin_node, &kp));
+    if (g->map_version != h->map_version) {
+        MeasureArgs a = update_measure_args(h, nullptr, cap, true);
+        MeasureKernelShape shape[3];
+        measure_kernel_shapes(a, measure_grid((int)cap), shape);
+        void* margs[1] = {&a};
+        for (int k = 0; k < 3; ++k) {
+            cudaKernelNodeParams mp;
+            memset(&mp, 0, sizeof(mp));
+            mp.func = const_cast<void*>(shape[k].func);
+            mp.gridDim = dim3(shape[k].grid, 1, 1);
+            mp.blockDim = dim3(shape[k].block, 1, 1);
+            mp.kernelParams = margs;
+            for (cudaGraphNode_t nd : g->measure_nodes[k]) LV_CUDA(cudaGraphExecKernelNodeSetParams(g->exec, nd, &mp));
+        }
+        g->map_version = h->map_version;
+    }
+    LV_CUDA(cudaGraphLaunch(g->exec, h->stream));
+    h->prof.total_launches += 1 + 4 * (h->prm.MAX_NUM_ITERS + 1);
+    return LV_OK;
+}
+
+static lv_status enqueue_update_kernels(lv_context* h, const float* d_xyz, int64_t n, bool as_job) {
+    LV_CUDA(launch_ieskf_begin(h->d_ctrl, as_job ? h->d_job : nullptr, d_xyz, (int)n, h->stream));
+    if (!as_job) h->prof.total_launches += 1;
+    MeasureArgs a = update_measure_args(h, d_xyz, n, as_job);
     const int grid = measure_grid((int)n);
     for (int e = 0; e <= h->prm.MAX_NUM_ITERS; ++e) {            /* i = -1 .. max_iter-1, esekfom.hpp:1634 */
         EventPair ep;
-        bool pr = prof_begin(h, 0, &ep);
-        ep.upd = (int)(h->update_seq % kNevalsRing); ep.slot = e;
-        LV_CUDA(launch_measure(a, grid, h->stream));
-        if (pr) prof_end(h, &ep);
+        bool pr;
+        if (h->profile && !as_job) {     /* one event pair per measurement kernel */
+            struct Ctx { lv_context* h; EventPair ep; bool on; int upd, slot; } ctx = {h, EventPair(), false, (int)(h->update_seq % kNevalsRing), e};
+            MeasureProbe probe;
+            probe.ctx = &ctx;
+            probe.at = [](void* p, int stage) {
+                Ctx* c = static_cast<Ctx*>(p);
+                if (stage > 0 && c->on) prof_end(c->h, &c->ep);
+                c->on = false;
+                if (stage < 3) {
+                    c->on = prof_begin(c->h, 3 + stage, &c->ep);
+                    c->ep.upd = c->upd; c->ep.slot = c->slot;
+                }
+            };
+            LV_CUDA(launch_measure(a, grid, h->stream, &probe));
+        } else {
+            LV_CUDA(launch_measure(a, grid, h->stream));
+        }
         pr = prof_begin(h, 1, &ep);
         ep.upd = (int)(h->update_seq % kNevalsRing); ep.slot = e;
         LV_CUDA(launch_ieskf_step(h->d_ctrl, h->iprm, h->d_partials, grid, h->stream));
         if (pr) prof_end(h, &ep);
-        h->prof.total_launches += 4;
+        if (!as_job) h->prof.total_launches += 4;
     }
     if (h->profile) {
         LV_CUDA(cudaMemcpyAsync(&h->h_nevals[h->update_seq % kNevalsRing], &h->d_ctrl->n_evals, sizeof(int32_t),

@@ -14,11 +14,20 @@ namespace lv {
 
 enum { kMeasureThreads = 128, kPartialStride = 96, kStepThreads = 512 };
 
+/* the sweep of an update replayed from a CUDA graph: written by the begin kernel (whose arguments are the
+ * only thing patched per launch), read by the measurement kernels instead of MeasureArgs::xyz / n / n_tiles */
+struct MeasureJob {
+    const float* xyz;
+    int32_t n;
+    int32_t n_tiles;
+};
+
 /* per-launch constants of the fused measure kernel */
 struct MeasureArgs {
     const float* xyz;          /* n x 3 packed, LiDAR frame                               */
-    int32_t n;
+    int32_t n;                 /* with `job`: the capacity the grids were sized for       */
     int32_t n_tiles;           /* ceil(n / kMeasureThreads)                               */
+    const MeasureJob* job;     /* non-NULL: xyz / n / n_tiles come from device memory      */
     VoxelMapView map;
     const UpdateCtrl* ctrl;    /* frame + done flag                                       */
     UpdateCtrl* prep;          /* non-NULL: block 0 of the fit kernel runs ieskf_prepare() */
@@ -79,8 +88,17 @@ cudaError_t map_rebuild(MapBuffers& b, cudaStream_t st, int* launches);
 VoxelMapView map_view(const MapBuffers& b);
 
 int measure_grid(int n);
-cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st);
-cudaError_t launch_ieskf_begin(UpdateCtrl* c, cudaStream_t st);
+/* `probe` (optional) is called on the launching thread before the search (stage 0), after it (1), after the
+ * upper-level search (2) and after the fit (3): the profiler records its events there */
+struct MeasureProbe { void (*at)(void* ctx, int stage); void* ctx; };
+cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st, const MeasureProbe* probe = nullptr);
+cudaError_t launch_ieskf_begin(UpdateCtrl* c, MeasureJob* job, const float* xyz, int n, cudaStream_t st);
+const void* ieskf_begin_kernel_ptr();
+void measure_init();                          /* constant tables; call once before any capture           */
+/* the three kernels of launch_measure() (search instance, search-upper, fit) with their launch shapes, for
+ * patching the nodes of a captured update when the map view changes */
+struct MeasureKernelShape { const void* func; unsigned grid, block; };
+void measure_kernel_shapes(const MeasureArgs& a, int grid, MeasureKernelShape out[3]);
 cudaError_t launch_ieskf_step(UpdateCtrl* c, const IeskfParams& prm, const double* partials, int n_partials,
                               cudaStream_t st);
 /* stand-alone reduction of the partials (operator-boundary calls): out[0:144) HTH, [144:156) HTh, [156] Nm */

@@ -50,6 +50,15 @@ static void init_pairs() {
     g_pairs_ready = true;
 }
 
+/* the sweep of this launch: kernel arguments, or the device-side job of a graph replay */
+struct JobView { const float* xyz; int n; int n_tiles; };
+__device__ __forceinline__ JobView job_view(const MeasureArgs& a) {
+    JobView j;
+    if (a.job) { j.xyz = a.job->xyz; j.n = a.job->n; j.n_tiles = a.job->n_tiles; }
+    else { j.xyz = a.xyz; j.n = a.n; j.n_tiles = a.n_tiles; }
+    return j;
+}
+
 #define LV_ROW_STRIDE (kMeasureThreads + 1)   /* +1 double: 13 row-columns land in distinct banks */
 #define LV_SEARCH_THREADS 128
 #define LV_GROUP 4                              /* lanes per query in K1 (LV_SEARCH_GROUP=1|2|4|8 overrides) */
@@ -84,13 +93,14 @@ __global__ void __launch_bounds__(LV_SEARCH_THREADS) lv_search_kernel(const Meas
     if (a.ctrl->done) return;   /* update already finished (uniform over the grid) */
     typedef GroupLanes<G> Grp;
     const Rt32& T = a.ctrl->frame.lidar_to_world;       /* uniform loads */
+    const JobView jb = job_view(a);
     const int qi = (int)(((int64_t)blockIdx.x * LV_SEARCH_THREADS + threadIdx.x) / G);
-    const bool have = qi < a.n;
+    const bool have = qi < jb.n;
     float g[3] = {0.f, 0.f, 0.f};
     uint32_t bs = 0, bc = 0;
     int st = 0;                       /* 0 no query / not finite, 1 bucket, 2 no level-0 slot */
     if (have) {
-        rt_apply(T, a.xyz[3 * qi], a.xyz[3 * qi + 1], a.xyz[3 * qi + 2], g);   /* Mapper.cpp:51 */
+        rt_apply(T, jb.xyz[3 * qi], jb.xyz[3 * qi + 1], jb.xyz[3 * qi + 2], g);   /* Mapper.cpp:51 */
         const bool finite = (fabsf(g[0]) < 1e9f) && (fabsf(g[1]) < 1e9f) && (fabsf(g[2]) < 1e9f);
         if (finite) st = level0_probe(a.map, g[0], g[1], g[2], &bs, &bc) ? 1 : 2;
     }
@@ -109,12 +119,13 @@ __global__ void __launch_bounds__(LV_SEARCH_THREADS) lv_search_kernel(const Meas
 __global__ void __launch_bounds__(128) lv_search_upper_kernel(const MeasureArgs a) {
     if (a.ctrl->done) return;
     const uint32_t n_hard = *a.hard_count;
+    const JobView jb = job_view(a);
     const Rt32& T = a.ctrl->frame.lidar_to_world;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t h = warp; h < n_hard; h += n_warps) {
         const int qi = (int)a.hard_list[h];
         float g[3];
-        rt_apply(T, a.xyz[3 * qi], a.xyz[3 * qi + 1], a.xyz[3 * qi + 2], g);
+        rt_apply(T, jb.xyz[3 * qi], jb.xyz[3 * qi + 1], jb.xyz[3 * qi + 2], g);
         const int2 prev = a.nn_b[qi];   /* level 0's (uncertified) 5th distance bounds the answer from above */
         Top5 u;
         knn5_upper<GroupWarp>(a.map, g[0], g[1], g[2], a.max_d2, prev.x >= 0 ? __int_as_float(prev.y) : a.max_d2, u);
@@ -157,16 +168,17 @@ __global__ void __launch_bounds__(kMeasureThreads, 4) lv_fit_kernel(const Measur
     __syncthreads();
 
     const int tid = threadIdx.x;
+    const JobView jb = job_view(a);
     double acc = 0.0;
     int count = 0;
 
-    for (int tile = bid; tile < a.n_tiles; tile += n_blocks) {
+    for (int tile = bid; tile < jb.n_tiles; tile += n_blocks) {
         const int i = tile * kMeasureThreads + tid;
         bool chosen = false;
         double row[12], hval = 0.0;
-        if (i < a.n) {
+        if (i < jb.n) {
             float g[3];
-            rt_apply(s_frame.lidar_to_world, a.xyz[3 * i], a.xyz[3 * i + 1], a.xyz[3 * i + 2], g);
+            rt_apply(s_frame.lidar_to_world, jb.xyz[3 * i], jb.xyz[3 * i + 1], jb.xyz[3 * i + 2], g);
             const int4 na = a.nn_a[i];
             const int2 nb = a.nn_b[i];
             const float d4 = __int_as_float(nb.y);
@@ -330,7 +342,12 @@ __global__ void __launch_bounds__(kStepThreads) lv_reduce_partials_kernel(const 
     if (threadIdx.x == 0) out[156] = (double)nm;
 }
 
-__global__ void __launch_bounds__(256) lv_ieskf_begin_kernel(UpdateCtrl* c) {
+__global__ void __launch_bounds__(256) lv_ieskf_begin_kernel(UpdateCtrl* c, MeasureJob* job, const float* xyz, int n) {
+    if (job && threadIdx.x == 0) {
+        job->xyz = xyz;
+        job->n = n;
+        job->n_tiles = (n + kMeasureThreads - 1) / kMeasureThreads;
+    }
     ExecBlock ex;
     ieskf_begin(ex, c);
 }
@@ -355,31 +372,54 @@ int measure_grid(int n) {
     return tiles < cap ? (tiles > 0 ? tiles : 1) : cap;
 }
 
-cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st) {
-    init_pairs();
-    static int group = 0;   /* lanes per query in K1; LV_SEARCH_GROUP overrides for tuning runs */
+void measure_init() { init_pairs(); }
+
+static int search_group() {   /* lanes per query in K1; LV_SEARCH_GROUP overrides for tuning runs */
+    static int group = 0;
     if (!group) {
         const char* e = getenv("LV_SEARCH_GROUP");
         group = e ? atoi(e) : LV_GROUP;
         if (group != 1 && group != 2 && group != 4 && group != 8) group = LV_GROUP;
     }
-    int sgrid = (int)(((int64_t)a.n * group + LV_SEARCH_THREADS - 1) / LV_SEARCH_THREADS);
-    if (sgrid < 1) sgrid = 1;
+    return group;
+}
+static int search_grid(const MeasureArgs& a, int group) {
+    const int sgrid = (int)(((int64_t)a.n * group + LV_SEARCH_THREADS - 1) / LV_SEARCH_THREADS);
+    return sgrid < 1 ? 1 : sgrid;
+}
+void measure_kernel_shapes(const MeasureArgs& a, int grid, MeasureKernelShape out[3]) {
+    const int group = search_group();
+    out[0].func = group == 1 ? (const void*)lv_search_kernel<1> : group == 2 ? (const void*)lv_search_kernel<2>
+                : group == 8 ? (const void*)lv_search_kernel<8> : (const void*)lv_search_kernel<4>;
+    out[0].grid = (unsigned)search_grid(a, group); out[0].block = LV_SEARCH_THREADS;
+    out[1].func = (const void*)lv_search_upper_kernel; out[1].grid = 148 * 2; out[1].block = 128;
+    out[2].func = (const void*)lv_fit_kernel; out[2].grid = (unsigned)(grid + (a.prep ? 1 : 0)); out[2].block = kMeasureThreads;
+}
+
+cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st, const MeasureProbe* probe) {
+    init_pairs();
+    const int group = search_group();
+    const int sgrid = search_grid(a, group);
     cudaMemsetAsync(a.hard_count, 0, sizeof(uint32_t), st);
+    if (probe) probe->at(probe->ctx, 0);
     switch (group) {
         case 1: lv_search_kernel<1><<<sgrid, LV_SEARCH_THREADS, 0, st>>>(a); break;
         case 2: lv_search_kernel<2><<<sgrid, LV_SEARCH_THREADS, 0, st>>>(a); break;
         case 8: lv_search_kernel<8><<<sgrid, LV_SEARCH_THREADS, 0, st>>>(a); break;
         default: lv_search_kernel<4><<<sgrid, LV_SEARCH_THREADS, 0, st>>>(a); break;
     }
+    if (probe) probe->at(probe->ctx, 1);
     lv_search_upper_kernel<<<148 * 2, 128, 0, st>>>(a);
+    if (probe) probe->at(probe->ctx, 2);
     lv_fit_kernel<<<grid + (a.prep ? 1 : 0), kMeasureThreads, 0, st>>>(a);
+    if (probe) probe->at(probe->ctx, 3);
     return cudaGetLastError();
 }
-cudaError_t launch_ieskf_begin(UpdateCtrl* c, cudaStream_t st) {
-    lv_ieskf_begin_kernel<<<1, 256, 0, st>>>(c);
+cudaError_t launch_ieskf_begin(UpdateCtrl* c, MeasureJob* job, const float* xyz, int n, cudaStream_t st) {
+    lv_ieskf_begin_kernel<<<1, 256, 0, st>>>(c, job, xyz, n);
     return cudaGetLastError();
 }
+const void* ieskf_begin_kernel_ptr() { return (const void*)lv_ieskf_begin_kernel; }
 cudaError_t launch_ieskf_step(UpdateCtrl* c, const IeskfParams& prm, const double* partials, int n_partials,
                               cudaStream_t st) {
     init_pairs();
