@@ -107,6 +107,7 @@ typedef struct lv_profile {
     double search_ms;         /* lv_search_kernel: exact 5-NN at level 0                   */
     double search_upper_ms;   /* lv_search_upper_kernel: the queries level 0 cannot certify */
     double fit_ms;            /* lv_fit_kernel: plane fit, Jacobian rows, normal equations  */
+    double reuse_ms;          /* lv_reuse_kernel: neighbours carried over from the previous evaluation */
 } lv_profile;
 
 /* ------------------------------------------------------------------------------------------ */

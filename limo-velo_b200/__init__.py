@@ -49,7 +49,8 @@ class Profile(C.Structure):
     _fields_ = [("measure_ms", C.c_double), ("solve_ms", C.c_double), ("build_ms", C.c_double),
                 ("measure_launches", C.c_int64), ("solve_launches", C.c_int64), ("build_launches", C.c_int64),
                 ("total_launches", C.c_int64), ("idle_ms", C.c_double), ("idle_launches", C.c_int64),
-                ("search_ms", C.c_double), ("search_upper_ms", C.c_double), ("fit_ms", C.c_double)]
+                ("search_ms", C.c_double), ("search_upper_ms", C.c_double), ("fit_ms", C.c_double),
+                ("reuse_ms", C.c_double)]
 
 
 def build(verbose=False):

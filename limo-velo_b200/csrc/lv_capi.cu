@@ -53,7 +53,10 @@ struct lv_context {
     double* d_partials = nullptr;
     int4* d_nn_a = nullptr;            /* max_points: K1 -> K2 hand-over */
     int2* d_nn_b = nullptr;
-    uint32_t* d_hard_list = nullptr;   /* max_points + 1: work list of K1b and its length */
+    uint32_t* d_hard_list = nullptr;   /* max_points + 3: work list of K1b, its length, search cursor, redo length */
+    float4* d_ref = nullptr;           /* max_points: reuse reference (lv_reuse_kernel) */
+    uint32_t* d_redo = nullptr;        /* max_points */
+    bool use_reuse = true;
     double* d_reduced = nullptr;       /* 157 doubles */
     double* h_reduced = nullptr;       /* pinned */
     void* d_flush = nullptr;
@@ -84,7 +87,7 @@ struct lv_context {
         cudaGraph_t graph;
         cudaGraphExec_t exec;
         cudaGraphNode_t begin_node;
-        std::vector<cudaGraphNode_t> measure_nodes[3];   /* search, search-upper, fit: they carry the map view */
+        std::vector<cudaGraphNode_t> measure_nodes[kMeasureKernels];   /* they carry the map view */
         uint64_t map_version;
     };
     std::vector<UpdateGraph> graphs;
@@ -106,6 +109,7 @@ static lv_status drain_events(lv_context* h) {
         else if (e.kind == 3) { h->prof.search_ms += ms; h->prof.measure_ms += ms; h->prof.measure_launches++; }
         else if (e.kind == 4) { h->prof.search_upper_ms += ms; h->prof.measure_ms += ms; }
         else if (e.kind == 5) { h->prof.fit_ms += ms; h->prof.measure_ms += ms; }
+        else if (e.kind == 6) { h->prof.reuse_ms += ms; h->prof.measure_ms += ms; }
         else if (e.kind == 1) { h->prof.solve_ms += ms; h->prof.solve_launches++; }
         else { h->prof.build_ms += ms; h->prof.build_launches++; }
         h->pool.push_back(e);
@@ -224,7 +228,10 @@ lv_status lv_create(const lv_params* p, lv_handle* out) {
     LV_CUDA(cudaMalloc(&h->d_sweep, sizeof(float) * 3 * p->max_points));
     LV_CUDA(cudaMalloc(&h->d_nn_a, sizeof(int4) * p->max_points));
     LV_CUDA(cudaMalloc(&h->d_nn_b, sizeof(int2) * p->max_points));
-    LV_CUDA(cudaMalloc(&h->d_hard_list, sizeof(uint32_t) * (p->max_points + 1)));
+    LV_CUDA(cudaMalloc(&h->d_hard_list, sizeof(uint32_t) * (p->max_points + 3)));
+    LV_CUDA(cudaMalloc(&h->d_ref, sizeof(float4) * p->max_points));
+    LV_CUDA(cudaMalloc(&h->d_redo, sizeof(uint32_t) * (p->max_points + 64)));   /* + one block of slack: read speculatively */
+    h->use_reuse = getenv("LV_NO_REUSE") == nullptr;
     LV_CUDA(cudaMalloc(&h->d_job, sizeof(MeasureJob)));
     measure_init();
     h->use_graph = getenv("LV_NO_GRAPH") == nullptr;
@@ -251,7 +258,7 @@ void lv_destroy(lv_handle h) {
     for (auto& e : h->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : h->pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& u : h->graphs) { cudaGraphExecDestroy(u.exec); cudaGraphDestroy(u.graph); }
-    cudaFree(h->d_job);
+    cudaFree(h->d_job); cudaFree(h->d_ref); cudaFree(h->d_redo);
     MapBuffers& m = h->map;
     cudaFree(m.xyz); cudaFree(m.xyz_alt); cudaFree(m.keys); cudaFree(m.keys_sorted); cudaFree(m.vals); cudaFree(m.vals_sorted);
     cudaFree(m.pts);
@@ -371,11 +378,31 @@ static lv_status upload_state(lv_context* h, const double* x, const double* P) {
     return LV_OK;
 }
 
+/* launch_measure() with one CUDA-event pair per kernel when profiling is on (never inside a capture) */
+static cudaError_t launch_measure_timed(lv_context* h, const MeasureArgs& a, int grid, int allow_events, int reuse,
+                                        int upd, int slot) {
+    if (!h->profile || !allow_events) return launch_measure(a, grid, h->stream, nullptr, reuse);
+    struct Ctx { lv_context* h; EventPair ep; bool on; int upd, slot; } ctx = {h, EventPair(), false, upd, slot};
+    MeasureProbe probe;
+    probe.ctx = &ctx;
+    probe.at = [](void* p, int stage) {
+        Ctx* c = static_cast<Ctx*>(p);
+        if (c->on) prof_end(c->h, &c->ep);
+        c->on = false;
+        if (stage != 3) {         /* 4: reuse kernel follows, 0: search, 1: search-upper, 2: fit, 3: end */
+            c->on = prof_begin(c->h, stage == 4 ? 6 : 3 + stage, &c->ep);
+            c->ep.upd = c->upd; c->ep.slot = c->slot;
+        }
+    };
+    return launch_measure(a, grid, h->stream, &probe, reuse);
+}
+
 /* ---- the update ------------------------------------------------------------------------------ */
 static MeasureArgs update_measure_args(lv_context* h, const float* d_xyz, int64_t n, bool as_job) {
     MeasureArgs a = make_measure_args(h, d_xyz, n);
     a.prep = h->d_ctrl;                                           /* ieskf_prepare rides in the fit kernel */
     if (as_job) a.job = h->d_job;
+    if (h->use_reuse) { a.ref = h->d_ref; a.redo_list = h->d_redo; }
     return a;
 }
 
@@ -399,7 +426,7 @@ static lv_status build_update_graph(lv_context* h, int64_t cap, lv_context::Upda
     /* nodes patched per launch: the begin kernel (sweep pointer and size) and, after a map update, the
      * measurement kernels (their arguments embed the map view) */
     MeasureArgs a = update_measure_args(h, nullptr, cap, true);
-    MeasureKernelShape shape[3];
+    MeasureKernelShape shape[kMeasureKernels];
     measure_kernel_shapes(a, measure_grid((int)cap), shape);
     size_t n_nodes = 0;
     LV_CUDA(cudaGraphGetNodes(graph, nullptr, &n_nodes));
@@ -413,12 +440,12 @@ static lv_status build_update_graph(lv_context* h, int64_t cap, lv_context::Upda
         cudaKernelNodeParams kp;
         LV_CUDA(cudaGraphKernelNodeGetParams(nd, &kp));
         if (kp.func == ieskf_begin_kernel_ptr()) out->begin_node = nd;
-        for (int k = 0; k < 3; ++k)
+        for (int k = 0; k < kMeasureKernels; ++k)
             if (kp.func == shape[k].func) out->measure_nodes[k].push_back(nd);
     }
     const size_t evals = (size_t)h->prm.MAX_NUM_ITERS + 1;
-    if (!out->begin_node || out->measure_nodes[0].size() != evals || out->measure_nodes[1].size() != evals ||
-        out->measure_nodes[2].size() != evals) {
+    if (!out->begin_node || out->measure_nodes[0].size() + out->measure_nodes[3].size() != evals ||
+        out->measure_nodes[1].size() != evals || out->measure_nodes[2].size() != evals) {
         set_error("update graph: unexpected node set");
         return LV_ERR_CUDA;
     }
@@ -457,10 +484,10 @@ static lv_status enqueue_update(lv_context* h, const float* d_xyz, int64_t n) {
     LV_CUDA(cudaGraphExecKernelNodeSetParams(g->exec, g->begin_node, &kp));
     if (g->map_version != h->map_version) {
         MeasureArgs a = update_measure_args(h, nullptr, cap, true);
-        MeasureKernelShape shape[3];
+        MeasureKernelShape shape[kMeasureKernels];
         measure_kernel_shapes(a, measure_grid((int)cap), shape);
         void* margs[1] = {&a};
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < kMeasureKernels; ++k) {
             cudaKernelNodeParams mp;
             memset(&mp, 0, sizeof(mp));
             mp.func = const_cast<void*>(shape[k].func);
@@ -472,7 +499,7 @@ static lv_status enqueue_update(lv_context* h, const float* d_xyz, int64_t n) {
         g->map_version = h->map_version;
     }
     LV_CUDA(cudaGraphLaunch(g->exec, h->stream));
-    h->prof.total_launches += 1 + 4 * (h->prm.MAX_NUM_ITERS + 1);
+    h->prof.total_launches += 1 + 4 * (h->prm.MAX_NUM_ITERS + 1) + (h->use_reuse ? h->prm.MAX_NUM_ITERS : 0);
     return LV_OK;
 }
 
@@ -484,28 +511,12 @@ static lv_status enqueue_update_kernels(lv_context* h, const float* d_xyz, int64
     for (int e = 0; e <= h->prm.MAX_NUM_ITERS; ++e) {            /* i = -1 .. max_iter-1, esekfom.hpp:1634 */
         EventPair ep;
         bool pr;
-        if (h->profile && !as_job) {     /* one event pair per measurement kernel */
-            struct Ctx { lv_context* h; EventPair ep; bool on; int upd, slot; } ctx = {h, EventPair(), false, (int)(h->update_seq % kNevalsRing), e};
-            MeasureProbe probe;
-            probe.ctx = &ctx;
-            probe.at = [](void* p, int stage) {
-                Ctx* c = static_cast<Ctx*>(p);
-                if (stage > 0 && c->on) prof_end(c->h, &c->ep);
-                c->on = false;
-                if (stage < 3) {
-                    c->on = prof_begin(c->h, 3 + stage, &c->ep);
-                    c->ep.upd = c->upd; c->ep.slot = c->slot;
-                }
-            };
-            LV_CUDA(launch_measure(a, grid, h->stream, &probe));
-        } else {
-            LV_CUDA(launch_measure(a, grid, h->stream));
-        }
+        LV_CUDA(launch_measure_timed(h, a, grid, as_job ? 0 : 1, e > 0, (int)(h->update_seq % kNevalsRing), e));
         pr = prof_begin(h, 1, &ep);
         ep.upd = (int)(h->update_seq % kNevalsRing); ep.slot = e;
         LV_CUDA(launch_ieskf_step(h->d_ctrl, h->iprm, h->d_partials, grid, h->stream));
         if (pr) prof_end(h, &ep);
-        if (!as_job) h->prof.total_launches += 4;
+        if (!as_job) h->prof.total_launches += 4 + ((e > 0 && h->use_reuse) ? 1 : 0);
     }
     if (h->profile) {
         LV_CUDA(cudaMemcpyAsync(&h->h_nevals[h->update_seq % kNevalsRing], &h->d_ctrl->n_evals, sizeof(int32_t),
@@ -587,10 +598,7 @@ static lv_status run_measure_once(lv_context* h, const double* x, const float* x
         a.g_world = h->d_gworld;
     }
     const int grid = measure_grid((int)n);
-    EventPair ep;
-    const bool pr = prof_begin(h, 0, &ep);
-    LV_CUDA(launch_measure(a, grid, h->stream));
-    if (pr) prof_end(h, &ep);
+    LV_CUDA(launch_measure_timed(h, a, grid, 1, 0, -1, 0));
     LV_CUDA(launch_reduce_partials(h->d_partials, grid, h->d_reduced, h->stream));
     LV_CUDA(cudaMemcpyAsync(h->h_reduced, h->d_reduced, sizeof(double) * 157, cudaMemcpyDeviceToHost, h->stream));
     h->prof.total_launches += 5;

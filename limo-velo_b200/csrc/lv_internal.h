@@ -48,7 +48,10 @@ struct MeasureArgs {
     int4* nn_a;                /* n: search result handed from K1 to K2 (neighbours 0..3)      */
     int2* nn_b;                /* n: (neighbour 4, bits of the 5th squared distance)         */
     uint32_t* hard_list;       /* n: queries level 0 could not certify (K1 -> K1b)           */
-    uint32_t* hard_count;
+    uint32_t* hard_count;      /* [0] length of hard_list, [1] cursor of the persistent search, [2] length of redo_list */
+    /* reuse of neighbours across the evaluations of one update (NULL: off) */
+    float4* ref;               /* n: world position the stored neighbours were searched from + outsider bound */
+    uint32_t* redo_list;       /* n: queries whose neighbours could not be reused (Kv -> K1)  */
 };
 
 /* one level of the voxel pyramid */
@@ -91,14 +94,18 @@ int measure_grid(int n);
 /* `probe` (optional) is called on the launching thread before the search (stage 0), after it (1), after the
  * upper-level search (2) and after the fit (3): the profiler records its events there */
 struct MeasureProbe { void (*at)(void* ctx, int stage); void* ctx; };
-cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st, const MeasureProbe* probe = nullptr);
+/* reuse != 0 (needs a.ref, evaluations after the first of an update): lv_reuse_kernel first, then the search only
+ * over the queries it could not vouch for; the probe then sees stage 4 before the reuse kernel */
+cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st, const MeasureProbe* probe = nullptr,
+                           int reuse = 0);
 cudaError_t launch_ieskf_begin(UpdateCtrl* c, MeasureJob* job, const float* xyz, int n, cudaStream_t st);
 const void* ieskf_begin_kernel_ptr();
 void measure_init();                          /* constant tables; call once before any capture           */
 /* the three kernels of launch_measure() (search instance, search-upper, fit) with their launch shapes, for
  * patching the nodes of a captured update when the map view changes */
 struct MeasureKernelShape { const void* func; unsigned grid, block; };
-void measure_kernel_shapes(const MeasureArgs& a, int grid, MeasureKernelShape out[3]);
+enum { kMeasureKernels = 5 };   /* search, search-upper, fit, search over the redo list, reuse */
+void measure_kernel_shapes(const MeasureArgs& a, int grid, MeasureKernelShape out[kMeasureKernels]);
 cudaError_t launch_ieskf_step(UpdateCtrl* c, const IeskfParams& prm, const double* partials, int n_partials,
                               cudaStream_t st);
 /* stand-alone reduction of the partials (operator-boundary calls): out[0:144) HTH, [144:156) HTh, [156] Nm */

@@ -74,6 +74,10 @@ __device__ __forceinline__ void store_neighbours(const MeasureArgs& a, int qi, c
     a.nn_a[qi] = o;
     a.nn_b[qi] = make_int2(i4, __float_as_int(t.d4));
 }
+/* what a later evaluation needs to reuse this answer (lb <= 0: do not) */
+__device__ __forceinline__ void store_ref(const MeasureArgs& a, int qi, const float* g, float lb) {
+    if (a.ref) a.ref[qi] = make_float4(g[0], g[1], g[2], lb);
+}
 
 /*
  * K1 — search, level 0.  G lanes per query, ONE query per lane group, so the grid holds N * G / 32
@@ -88,14 +92,25 @@ __device__ __forceinline__ void store_neighbours(const MeasureArgs& a, int qi, c
  * that found them serialised up to 13 ring searches in one warp (firing order clusters them).
  * Output, 24 B per query: positions of the 5 neighbours and the 5th squared distance.
  */
-template <int G>
+template <int G, bool LIST>
 __global__ void __launch_bounds__(LV_SEARCH_THREADS) lv_search_kernel(const MeasureArgs a) {
-    if (a.ctrl->done) return;   /* update already finished (uniform over the grid) */
     typedef GroupLanes<G> Grp;
-    const Rt32& T = a.ctrl->frame.lidar_to_world;       /* uniform loads */
+    /* the search is a chain of dependent round trips (flags -> point -> slot -> bucket): everything that does
+     * not depend on an earlier answer is requested up front, the `done` test included */
+    const int done = a.ctrl->done;                      /* update already finished (uniform over the grid) */
+    const Rt32 T = a.ctrl->frame.lidar_to_world;        /* uniform loads */
     const JobView jb = job_view(a);
-    const int qi = (int)(((int64_t)blockIdx.x * LV_SEARCH_THREADS + threadIdx.x) / G);
-    const bool have = qi < jb.n;
+    const int n_redo = LIST ? (int)a.hard_count[2] : 0;
+    const int slot = (int)(((int64_t)blockIdx.x * LV_SEARCH_THREADS + threadIdx.x) / G);
+    const int listed = LIST ? (int)a.redo_list[slot] : 0;   /* redo_list holds max_points entries: always readable */
+    if (done) return;
+    int qi = slot;
+    bool have = slot < jb.n;
+    if (LIST) {                 /* only the queries lv_reuse_kernel handed back */
+        if ((int)blockIdx.x * (LV_SEARCH_THREADS / G) >= n_redo) return;
+        have = slot < n_redo;
+        qi = have ? listed : 0;
+    }
     float g[3] = {0.f, 0.f, 0.f};
     uint32_t bs = 0, bc = 0;
     int st = 0;                       /* 0 no query / not finite, 1 bucket, 2 no level-0 slot */
@@ -105,10 +120,101 @@ __global__ void __launch_bounds__(LV_SEARCH_THREADS) lv_search_kernel(const Meas
         if (finite) st = level0_probe(a.map, g[0], g[1], g[2], &bs, &bc) ? 1 : 2;
     }
     Top5 t;
-    const bool settled = level0_scan<Grp>(a.map, g[0], g[1], g[2], a.max_d2, bs, bc, st == 1, t);
+    float region = 0.f;
+    const bool settled = level0_scan<Grp>(a.map, g[0], g[1], g[2], a.max_d2, bs, bc, st == 1, t, &region);
     if (have && (threadIdx.x & (G - 1)) == 0) {
         store_neighbours(a, qi, t, false);
-        if (st == 2 || (st == 1 && !settled)) a.hard_list[atomicAdd(a.hard_count, 1u)] = (uint32_t)qi;
+        const bool hard = st == 2 || (st == 1 && !settled);
+        store_ref(a, qi, g, (st == 1 && settled) ? outsider_bound(t.d5, region) : 0.f);
+        if (hard) a.hard_list[atomicAdd(a.hard_count, 1u)] = (uint32_t)qi;
+    }
+}
+
+/*
+ * Kv — reuse.  Evaluations after the first of an update: the iterate moved by millimetres, the map not at all.
+ * One thread per query re-measures its five stored neighbours from the new world position and keeps them when
+ * query_reusable() proves the exact search would return the same five (lv_voxel_search.h); the others go to
+ * the redo list and through the search kernels as usual.  Results are identical either way.
+ */
+__global__ void __launch_bounds__(128) lv_reuse_kernel(const MeasureArgs a) {
+    if (a.ctrl->done) return;
+    const JobView jb = job_view(a);
+    const int qi = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    bool redo = false;
+    if (qi < jb.n) {
+        const Rt32& T = a.ctrl->frame.lidar_to_world;
+        float g[3];
+        rt_apply(T, jb.xyz[3 * qi], jb.xyz[3 * qi + 1], jb.xyz[3 * qi + 2], g);
+        const float4 r4 = a.ref[qi];
+        const int4 na = a.nn_a[qi];
+        const int2 nb = a.nn_b[qi];
+        redo = true;
+        if (r4.w > 0.f && nb.x != -1) {
+            const bool general = nb.x < -1;      /* positions in pts[] (stored as -2 - p) or in halo[] */
+            const float4* src = general ? a.map.pts : a.map.halo;
+            int id[5] = {na.x, na.y, na.z, na.w, nb.x};
+            float q[5][3];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                id[k] = general ? -2 - id[k] : id[k];
+                const float4 p = load_point(src + id[k]);
+                q[k][0] = p.x; q[k][1] = p.y; q[k][2] = p.z;
+            }
+            const float ref[4] = {r4.x, r4.y, r4.z, r4.w};
+            Top5 t;
+            if (query_reusable(ref, g, q, id, a.max_d2, t)) {
+                store_neighbours(a, qi, t, general);
+                redo = false;
+            }
+        }
+    }
+    /* one atomic per warp */
+    const unsigned m = __ballot_sync(0xffffffffu, redo);
+    if (m) {
+        const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(a.hard_count + 2, (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (redo) a.redo_list[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = (uint32_t)qi;
+    }
+}
+
+/*
+ * K1, persistent form: 148 x 12 resident blocks, every warp draws batches of 32 / G queries from a device
+ * counter until the sweep is exhausted.  Balances the SMs to within one batch instead of one block wave
+ * (the plain grid is 1.15 waves of 12 blocks per SM: ncu r1 shows SMs active 26 k .. 52 k cycles of 59 k).
+ */
+template <int G>
+__global__ void __launch_bounds__(LV_SEARCH_THREADS) lv_search_persistent_kernel(const MeasureArgs a) {
+    if (a.ctrl->done) return;
+    typedef GroupLanes<G> Grp;
+    const JobView jb = job_view(a);
+    const Rt32& T = a.ctrl->frame.lidar_to_world;
+    const int lane = threadIdx.x & 31;
+    uint32_t* counter = a.hard_count + 1;
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = (int)atomicAdd(counter, 32u / G);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= jb.n) break;
+        const int qi = base + lane / G;
+        const bool have = qi < jb.n;
+        float g[3] = {0.f, 0.f, 0.f};
+        uint32_t bs = 0, bc = 0;
+        int st = 0;
+        if (have) {
+            rt_apply(T, jb.xyz[3 * qi], jb.xyz[3 * qi + 1], jb.xyz[3 * qi + 2], g);
+            const bool finite = (fabsf(g[0]) < 1e9f) && (fabsf(g[1]) < 1e9f) && (fabsf(g[2]) < 1e9f);
+            if (finite) st = level0_probe(a.map, g[0], g[1], g[2], &bs, &bc) ? 1 : 2;
+        }
+        Top5 t;
+        float region = 0.f;
+        const bool settled = level0_scan<Grp>(a.map, g[0], g[1], g[2], a.max_d2, bs, bc, st == 1, t, &region);
+        if (have && (lane & (G - 1)) == 0) {
+            store_neighbours(a, qi, t, false);
+            store_ref(a, qi, g, (st == 1 && settled) ? outsider_bound(t.d5, region) : 0.f);
+            if (st == 2 || (st == 1 && !settled)) a.hard_list[atomicAdd(a.hard_count, 1u)] = (uint32_t)qi;
+        }
     }
 }
 
@@ -128,8 +234,12 @@ __global__ void __launch_bounds__(128) lv_search_upper_kernel(const MeasureArgs 
         rt_apply(T, jb.xyz[3 * qi], jb.xyz[3 * qi + 1], jb.xyz[3 * qi + 2], g);
         const int2 prev = a.nn_b[qi];   /* level 0's (uncertified) 5th distance bounds the answer from above */
         Top5 u;
-        knn5_upper<GroupWarp>(a.map, g[0], g[1], g[2], a.max_d2, prev.x >= 0 ? __int_as_float(prev.y) : a.max_d2, u);
-        if ((threadIdx.x & 31) == 0) store_neighbours(a, qi, u, true);
+        float region = 0.f;
+        knn5_upper<GroupWarp>(a.map, g[0], g[1], g[2], a.max_d2, prev.x >= 0 ? __int_as_float(prev.y) : a.max_d2, u, &region);
+        if ((threadIdx.x & 31) == 0) {
+            store_neighbours(a, qi, u, true);
+            store_ref(a, qi, g, outsider_bound(u.d5, region));
+        }
     }
 }
 
@@ -387,29 +497,50 @@ static int search_grid(const MeasureArgs& a, int group) {
     const int sgrid = (int)(((int64_t)a.n * group + LV_SEARCH_THREADS - 1) / LV_SEARCH_THREADS);
     return sgrid < 1 ? 1 : sgrid;
 }
-void measure_kernel_shapes(const MeasureArgs& a, int grid, MeasureKernelShape out[3]) {
+template <bool LIST>
+static const void* search_kernel_ptr(int group) {
+    return group == 1 ? (const void*)lv_search_kernel<1, LIST> : group == 2 ? (const void*)lv_search_kernel<2, LIST>
+         : group == 8 ? (const void*)lv_search_kernel<8, LIST> : (const void*)lv_search_kernel<4, LIST>;
+}
+void measure_kernel_shapes(const MeasureArgs& a, int grid, MeasureKernelShape out[kMeasureKernels]) {
     const int group = search_group();
-    out[0].func = group == 1 ? (const void*)lv_search_kernel<1> : group == 2 ? (const void*)lv_search_kernel<2>
-                : group == 8 ? (const void*)lv_search_kernel<8> : (const void*)lv_search_kernel<4>;
+    out[0].func = search_kernel_ptr<false>(group);
     out[0].grid = (unsigned)search_grid(a, group); out[0].block = LV_SEARCH_THREADS;
-    out[1].func = (const void*)lv_search_upper_kernel; out[1].grid = 148 * 2; out[1].block = 128;
+    out[1].func = (const void*)lv_search_upper_kernel; out[1].grid = 148 * 8; out[1].block = 128;
     out[2].func = (const void*)lv_fit_kernel; out[2].grid = (unsigned)(grid + (a.prep ? 1 : 0)); out[2].block = kMeasureThreads;
+    out[3].func = search_kernel_ptr<true>(group); out[3].grid = out[0].grid; out[3].block = LV_SEARCH_THREADS;
+    out[4].func = (const void*)lv_reuse_kernel; out[4].grid = (unsigned)((a.n + 127) / 128 > 0 ? (a.n + 127) / 128 : 1); out[4].block = 128;
 }
 
-cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st, const MeasureProbe* probe) {
+template <bool LIST>
+static void launch_search(const MeasureArgs& a, int group, int sgrid, cudaStream_t st) {
+    switch (group) {
+        case 1: lv_search_kernel<1, LIST><<<sgrid, LV_SEARCH_THREADS, 0, st>>>(a); break;
+        case 2: lv_search_kernel<2, LIST><<<sgrid, LV_SEARCH_THREADS, 0, st>>>(a); break;
+        case 8: lv_search_kernel<8, LIST><<<sgrid, LV_SEARCH_THREADS, 0, st>>>(a); break;
+        default: lv_search_kernel<4, LIST><<<sgrid, LV_SEARCH_THREADS, 0, st>>>(a); break;
+    }
+}
+
+cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st, const MeasureProbe* probe, int reuse) {
     init_pairs();
     const int group = search_group();
     const int sgrid = search_grid(a, group);
-    cudaMemsetAsync(a.hard_count, 0, sizeof(uint32_t), st);
-    if (probe) probe->at(probe->ctx, 0);
-    switch (group) {
-        case 1: lv_search_kernel<1><<<sgrid, LV_SEARCH_THREADS, 0, st>>>(a); break;
-        case 2: lv_search_kernel<2><<<sgrid, LV_SEARCH_THREADS, 0, st>>>(a); break;
-        case 8: lv_search_kernel<8><<<sgrid, LV_SEARCH_THREADS, 0, st>>>(a); break;
-        default: lv_search_kernel<4><<<sgrid, LV_SEARCH_THREADS, 0, st>>>(a); break;
+    /* work-list length, the persistent search's cursor, redo-list length */
+    cudaMemsetAsync(a.hard_count, 0, 3 * sizeof(uint32_t), st);
+    static const bool persist = getenv("LV_SEARCH_PERSIST") != nullptr;
+    if (reuse && a.ref) {
+        if (probe) probe->at(probe->ctx, 4);
+        lv_reuse_kernel<<<(a.n + 127) / 128 > 0 ? (a.n + 127) / 128 : 1, 128, 0, st>>>(a);
+        if (probe) probe->at(probe->ctx, 0);
+        launch_search<true>(a, group, sgrid, st);
+    } else {
+        if (probe) probe->at(probe->ctx, 0);
+        if (persist) lv_search_persistent_kernel<4><<<148 * 12, LV_SEARCH_THREADS, 0, st>>>(a);
+        else launch_search<false>(a, group, sgrid, st);
     }
     if (probe) probe->at(probe->ctx, 1);
-    lv_search_upper_kernel<<<148 * 2, 128, 0, st>>>(a);
+    lv_search_upper_kernel<<<148 * 8, 128, 0, st>>>(a);
     if (probe) probe->at(probe->ctx, 2);
     lv_fit_kernel<<<grid + (a.prep ? 1 : 0), kMeasureThreads, 0, st>>>(a);
     if (probe) probe->at(probe->ctx, 3);

@@ -40,6 +40,12 @@ struct float4 { float x, y, z, w; };
 struct uint4 { unsigned int x, y, z, w; };
 #endif
 
+#if defined(__CUDACC__)
+#define LV_UNROLL_N(n) _Pragma("unroll")
+#else
+#define LV_UNROLL_N(n)
+#endif
+
 namespace lv {
 
 enum { kMaxLevels = 4 };
@@ -137,15 +143,19 @@ LV_HD int voxel_find(const VoxelLevel& L, uint64_t key, uint32_t* start, uint32_
 struct Top5 {
     float d0, d1, d2, d3, d4;
     int i0, i1, i2, i3, i4;
+    float d5;   /* smallest squared distance seen that is NOT in the list (the 6th neighbour so far): feeds the
+                 * reuse test of later evaluations (query_reusable) */
 };
 LV_HD void top5_init(Top5& t, float bound) {
     t.d0 = t.d1 = t.d2 = t.d3 = t.d4 = bound;
     t.i0 = t.i1 = t.i2 = t.i3 = t.i4 = -1;
+    t.d5 = INFINITY;
 }
 /* insert if strictly better than the current 5th (ikd_Tree.cpp:1087: dist < q.top().dist);
  * equal distances keep the earlier candidate in front.                                      */
 LV_HD void top5_insert(Top5& t, float d, int id) {
-    if (!(d < t.d4)) return;
+    if (!(d < t.d4)) { t.d5 = d < t.d5 ? d : t.d5; return; }
+    t.d5 = t.d4 < t.d5 ? t.d4 : t.d5;   /* the old 5th drops out (a `bound` placeholder is >= every real candidate kept) */
     /* branch-free bubble through the sorted list: every lane of a warp executes the same selects */
     bool s;
     float td; int ti;
@@ -179,6 +189,8 @@ LV_HD void top5_pop(Top5& t, float bound) {
     t.d3 = t.d4; t.i3 = t.i4;
     t.d4 = bound; t.i4 = -1;
 }
+/* smallest distance this list still holds or has seen dropped: what a merge leaves behind */
+LV_HD float top5_rest(const Top5& t) { return t.d0 < t.d5 ? t.d0 : t.d5; }
 
 /* ---- lane groups: the rare queries level 0 cannot settle are finished by a whole warp ---------- */
 struct GroupSerial {   /* host / single lane */
@@ -186,6 +198,7 @@ struct GroupSerial {   /* host / single lane */
     LV_HD static int lane() { return 0; }
     LV_HD static uint32_t bcast(uint32_t v, int src) { (void)src; return v; }
     LV_HD static void merge(Top5& loc, float bound, Top5& out) { out = loc; (void)bound; }
+    LV_HD static float min_all(float v) { return v; }
 };
 #if defined(__CUDACC__)
 template <int G>
@@ -214,6 +227,12 @@ struct GroupLanes {    /* G consecutive lanes of a warp (G = 8 or 32); every lan
         }
         out.d0 = od[0]; out.d1 = od[1]; out.d2 = od[2]; out.d3 = od[3]; out.d4 = od[4];
         out.i0 = oi[0]; out.i1 = oi[1]; out.i2 = oi[2]; out.i3 = oi[3]; out.i4 = oi[4];
+        out.d5 = min_all(top5_rest(loc));   /* heads left after five extractions, and what the lanes dropped earlier */
+    }
+    __device__ __forceinline__ static float min_all(float v) {
+#pragma unroll
+        for (int s = 1; s < G; s <<= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, s));
+        return v;
     }
 };
 typedef GroupLanes<32> GroupWarp;
@@ -300,13 +319,21 @@ LV_HD bool level0_probe(const VoxelMapView& m, float gx, float gy, float gz, uin
 
 template <class Grp>
 LV_HD bool level0_scan(const VoxelMapView& m, float gx, float gy, float gz, float max_d2, uint32_t bstart, uint32_t bcount,
-                       bool active, Top5& out) {
+                       bool active, Top5& out, float* region_d2 = nullptr) {
     Top5 loc;
     top5_init(loc, max_d2);
     if (active) {
         const float4* p = m.halo + bstart;
         const uint32_t n = bcount, step = (uint32_t)Grp::size;
         uint32_t j = (uint32_t)Grp::lane();
+        /* eight, then four independent 16-byte loads in flight per lane: a typical bucket (~56 points over 4 lanes)
+         * takes two round trips instead of four (K1 is latency-bound: -11 % with the 8-wide step) */
+        for (; j + 7 * step < n; j += 8 * step) {
+            float4 q[8];
+            LV_UNROLL_N(8) for (int u = 0; u < 8; ++u) q[u] = load_point(p + j + (uint32_t)u * step);
+            LV_UNROLL_N(8) for (int u = 0; u < 8; ++u)
+                top5_insert(loc, sq_dist(gx, gy, gz, q[u].x, q[u].y, q[u].z), (int)(bstart + j + (uint32_t)u * step));
+        }
         for (; j + 3 * step < n; j += 4 * step) {   /* four independent 16-byte loads in flight per lane */
             const float4 q0 = load_point(p + j), q1 = load_point(p + j + step), q2 = load_point(p + j + 2 * step),
                          q3 = load_point(p + j + 3 * step);
@@ -323,7 +350,9 @@ LV_HD bool level0_scan(const VoxelMapView& m, float gx, float gy, float gz, floa
     Grp::merge(loc, max_d2, out);
     if (!active) return false;
     const uint32_t bx0 = voxel_coord(gx, m.inv_cell0), by0 = voxel_coord(gy, m.inv_cell0), bz0 = voxel_coord(gz, m.inv_cell0);
-    return out.d4 <= certified_d2(home_geom(m, 0, bx0, by0, bz0, gx, gy, gz));   /* out.d4 <= max_d2 always */
+    const float cert = certified_d2(home_geom(m, 0, bx0, by0, bz0, gx, gy, gz));
+    if (region_d2) *region_d2 = cert;     /* every map point outside the bucket is at least this far (squared) */
+    return out.d4 <= cert;                /* out.d4 <= max_d2 always */
 }
 
 /* strided scan: lane `first` of `step` lanes takes points first, first+step, ... */
@@ -348,19 +377,30 @@ LV_HD void scan_run_strided(const float4* p, uint32_t n, int base, uint32_t firs
  * Ids in `out` index pts[].
  */
 template <class Grp>
-LV_HD void knn5_upper(const VoxelMapView& m, float gx, float gy, float gz, float max_d2, float bound0, Top5& out) {
+LV_HD void knn5_upper(const VoxelMapView& m, float gx, float gy, float gz, float max_d2, float bound0, Top5& out,
+                      float* region_d2 = nullptr) {
     const uint32_t bx0 = voxel_coord(gx, m.inv_cell0), by0 = voxel_coord(gy, m.inv_cell0), bz0 = voxel_coord(gz, m.inv_cell0);
     const int last = m.n_levels - 1;
     int l = last > 0 ? 1 : 0;
+    float covered;     /* squared radius ring 1 of level l is guaranteed to contain */
     {
         float amax = fabsf(gx) > fabsf(gy) ? fabsf(gx) : fabsf(gy);
         amax = amax > fabsf(gz) ? amax : fabsf(gz);
         const float slack = 2e-6f * (amax + 4.0f);
         while (l < last && !(bound0 <= (m.lv[l].cell - slack) * (m.lv[l].cell - slack))) ++l;
+        covered = (m.lv[l].cell - slack) * (m.lv[l].cell - slack);
     }
-    /* strictly above bound0 so that the points level 0 saw are found again */
+    /* strictly above bound0 so that the points level 0 saw are found again; 10 % farther than needed (as far as
+     * the level covers) so that the answer comes with a margin to the nearest point NOT in it: later evaluations
+     * of the same sweep reuse it while the iterate moves less than that margin (query_reusable) */
     float bound = nextafterf(bound0, INFINITY);
+    {
+        float wide = bound0 * 1.21f;
+        wide = wide < covered ? wide : covered;
+        bound = bound > wide ? bound : wide;
+    }
     bound = bound < max_d2 ? bound : max_d2;
+    if (region_d2) *region_d2 = bound < covered ? bound : covered;
     const VoxelLevel& L = m.lv[l];
     const HomeGeom h = home_geom(m, l, bx0, by0, bz0, gx, gy, gz);
     const int hx = (int)(bx0 >> l), hy = (int)(by0 >> l), hz = (int)(bz0 >> l);
@@ -421,6 +461,49 @@ LV_HD void knn5_upper(const VoxelMapView& m, float gx, float gy, float gz, float
         if (voxel_find(L, voxel_key((uint32_t)cx, (uint32_t)cy, (uint32_t)cz), &s, &cnt) >= 0) scan_run(m.pts + s, cnt, (int)s, gx, gy, gz, loc);
     }
     Grp::merge(loc, bound, out);
+}
+
+/*
+ * Reuse of a query's neighbours by a later evaluation of the SAME sweep (the iterate moved, the map did not).
+ *   ref    (gx, gy, gz, lb): the world position the neighbours were searched from and lb, a lower bound (metres,
+ *          rounded down) of the distance from there to every map point that is not one of the five
+ *          (outsider_bound()).
+ *   g      the query's world position now; q[k], id[k] the five stored neighbours.
+ * A map point outside the five is now at least lb - |g - ref| away, so if the farthest of the five is closer
+ * than that (with room for the fp32 rounding of every computed distance) the exact search would return the
+ * same five: they only need their distances recomputed and their order restored.  Returns false (search
+ * again) on any doubt: fewer than five, a tie among the new distances, the 5th beyond the search radius.
+ */
+LV_HD float outsider_bound(float d5_sq, float region_sq) {
+    const float m = d5_sq < region_sq ? d5_sq : region_sq;
+    const float r = fsqrt(m > 0.f ? m : 0.f);
+    return r * (1.0f - 1e-6f);
+}
+LV_HD bool query_reusable(const float ref[4], const float g[3], const float (*q)[3], const int* id, float max_d2,
+                          Top5& out) {
+    if (!(ref[3] > 0.f)) return false;
+    float d[5];
+    int o[5];
+    for (int k = 0; k < 5; ++k) {
+        if (id[k] == -1) return false;
+        d[k] = sq_dist(g[0], g[1], g[2], q[k][0], q[k][1], q[k][2]);
+        o[k] = id[k];
+    }
+    /* 9-comparator sorting network for 5 keys */
+#define LV_CE(a, b) { if (d[b] < d[a]) { const float td = d[a]; d[a] = d[b]; d[b] = td; const int ti = o[a]; o[a] = o[b]; o[b] = ti; } }
+    LV_CE(0, 1) LV_CE(3, 4) LV_CE(2, 4) LV_CE(2, 3) LV_CE(0, 3) LV_CE(0, 2) LV_CE(1, 4) LV_CE(1, 3) LV_CE(1, 2)
+#undef LV_CE
+    if (d[0] == d[1] || d[1] == d[2] || d[2] == d[3] || d[3] == d[4]) return false;
+    if (!(d[4] < max_d2)) return false;
+    const float dx = g[0] - ref[0], dy = g[1] - ref[1], dz = g[2] - ref[2];
+    const float moved = fsqrt(dx * dx + dy * dy + dz * dz);
+    const float far5 = fsqrt(d[4]);
+    const float need = far5 + moved + 1e-5f * (far5 + moved + ref[3]) + 1e-5f;
+    if (!(need < ref[3])) return false;
+    out.d0 = d[0]; out.d1 = d[1]; out.d2 = d[2]; out.d3 = d[3]; out.d4 = d[4];
+    out.i0 = o[0]; out.i1 = o[1]; out.i2 = o[2]; out.i3 = o[3]; out.i4 = o[4];
+    out.d5 = INFINITY;
+    return true;
 }
 
 }  // namespace lv

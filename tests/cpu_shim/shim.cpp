@@ -299,6 +299,60 @@ int shim_sizeof_iterlog() { return (int)sizeof(IterLog); }
 
 }  // extern "C"
 
+/* neighbour reuse (query_reusable): search every query from state x0 keeping the reuse reference, then judge
+ * from state x1.  reused[i] = 1 when the stored five were vouched for; for those, same[i] = 1 iff a fresh search
+ * from x1 returns the same map points (by original index) with bit-identical distances in the same order. */
+extern "C" void shim_reuse_check(const ShimMap* sm, const double* x0, const double* x1, double max_dist, const float* xyz,
+                                 int64_t n, uint8_t* reused, uint8_t* same) {
+    Frame f0, f1;
+    make_frame(x0, &f0);
+    make_frame(x1, &f1);
+    const double gate = max_dist * max_dist;
+    float max_d2 = (float)gate;
+    if ((double)max_d2 < gate) max_d2 = nextafterf(max_d2, INFINITY);
+    auto search = [&](const float* g, Top5& t, float* lb) -> const float4* {
+        uint32_t bs, bc;
+        float region = 0.f;
+        const bool hb = level0_probe(sm->view, g[0], g[1], g[2], &bs, &bc);
+        if (level0_scan<GroupSerial>(sm->view, g[0], g[1], g[2], max_d2, bs, bc, hb, t, &region)) {
+            *lb = outsider_bound(t.d5, region);
+            return sm->view.halo;
+        }
+        const float bound0 = t.i4 >= 0 ? t.d4 : max_d2;
+        knn5_upper<GroupSerial>(sm->view, g[0], g[1], g[2], max_d2, bound0, t, &region);
+        *lb = outsider_bound(t.d5, region);
+        return sm->view.pts;
+    };
+    for (int64_t i = 0; i < n; ++i) {
+        float g0[3], g1[3];
+        rt_apply(f0.lidar_to_world, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], g0);
+        rt_apply(f1.lidar_to_world, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], g1);
+        Top5 t0, t1, tr;
+        float lb0 = 0.f, lb1 = 0.f;
+        const float4* src0 = search(g0, t0, &lb0);
+        const float ref[4] = {g0[0], g0[1], g0[2], lb0};
+        const int id[5] = {t0.i0, t0.i1, t0.i2, t0.i3, t0.i4};
+        float q[5][3];
+        for (int k = 0; k < 5; ++k)
+            if (id[k] >= 0) { q[k][0] = src0[id[k]].x; q[k][1] = src0[id[k]].y; q[k][2] = src0[id[k]].z; }
+        reused[i] = query_reusable(ref, g1, q, id, max_d2, tr) ? 1 : 0;
+        same[i] = 0;
+        if (!reused[i]) continue;
+        const float4* src1 = search(g1, t1, &lb1);
+        const int a[5] = {tr.i0, tr.i1, tr.i2, tr.i3, tr.i4}, b[5] = {t1.i0, t1.i1, t1.i2, t1.i3, t1.i4};
+        const float da[5] = {tr.d0, tr.d1, tr.d2, tr.d3, tr.d4}, db[5] = {t1.d0, t1.d1, t1.d2, t1.d3, t1.d4};
+        bool ok = true;
+        for (int k = 0; k < 5; ++k) {
+            if (b[k] < 0) { ok = false; break; }
+            int oa, ob;
+            memcpy(&oa, &src0[a[k]].w, 4);
+            memcpy(&ob, &src1[b[k]].w, 4);
+            ok = ok && oa == ob && da[k] == db[k];
+        }
+        same[i] = ok ? 1 : 0;
+    }
+}
+
 /* diagnostics: which queries level 0 settles */
 extern "C" void shim_query_stats(const ShimMap* sm, const double* x, const float* xyz, int64_t n, double max_dist,
                                  int32_t* level_out, int32_t* scanned_out) {

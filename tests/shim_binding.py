@@ -84,6 +84,15 @@ class ShimMap:
                               _f(out["nn_sqd"]), _f(out["plane"]), _f(out["dist"]), _f(out["g"]), _d(out["rows"]))
         return out
 
+    def reuse_check(self, x0, x1, xyz, max_dist=2.0):
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        n = xyz.shape[0]
+        reused, same = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+        self.L.shim_reuse_check(C.c_void_p(self.h), _d(np.ascontiguousarray(x0, np.float64)),
+                                _d(np.ascontiguousarray(x1, np.float64)), C.c_double(max_dist), _f(xyz), C.c_int64(n),
+                                reused.ctypes.data_as(C.c_void_p), same.ctypes.data_as(C.c_void_p))
+        return reused.astype(bool), same.astype(bool)
+
     def update(self, x, P, prm, xyz):
         xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
         x = np.array(x, np.float64).copy()

@@ -137,3 +137,31 @@ def test_manifold_and_plane_helpers_match_oracle(O):
         pb, okb = S.plane_fit(pts, 0.05)
         assert oka == okb and (np.isnan(pa) == np.isnan(pb)).all()
         assert (pa[~np.isnan(pa)] == pb[~np.isnan(pb)]).all()
+
+
+@pytest.mark.parametrize("cell", [0.5, 0.3])
+def test_neighbour_reuse_is_exact(O, scene_xaloc, cell):
+    """query_reusable (lv_reuse_kernel): whenever it vouches for the neighbours found from an earlier iterate, a
+    fresh exact search from the new iterate returns the same five points with bit-identical distances"""
+    sc = scene_xaloc
+    sm = S.ShimMap(sc.map, cell, sc.prm.MAX_DIST_PLANE)
+    rates = []
+    for pos, rot in ((0.0, 0.0), (2e-4, 1e-5), (3e-3, 1e-4), (2e-2, 5e-4), (8e-2, 5e-3), (0.5, 2e-2)):
+        d = np.zeros(23)
+        d[0:3] = [pos, -0.7 * pos, 0.4 * pos]
+        d[3:6] = [rot, 0.5 * rot, -rot]
+        x1 = O.boxplus(sc.x_prop, d)
+        reused, same = sm.reuse_check(sc.x_prop, x1, sc.sweep, sc.prm.MAX_DIST_PLANE)
+        assert same[reused].all(), (pos, rot, int((~same[reused]).sum()))
+        rates.append(reused.mean())
+    assert rates[0] > 0.8 and rates[1] > 0.7          # millimetre moves keep most answers
+    assert rates[-1] < 0.2                             # half a metre keeps (almost) none
+    assert all(a >= b - 0.02 for a, b in zip(rates, rates[1:]))
+    # shifted off the surfaces: sparse buckets, upper-level answers, fewer than five neighbours
+    for shift in ([0, 0, 0.7], [0, 0, 1.6], [0.4, 0.4, 0.4]):
+        q = sc.sweep[:4000] + np.float32(shift)
+        for mv in (1e-3, 2e-2):
+            d = np.zeros(23)
+            d[0:3] = mv
+            reused, same = sm.reuse_check(sc.x_prop, O.boxplus(sc.x_prop, d), q, sc.prm.MAX_DIST_PLANE)
+            assert same[reused].all()

@@ -68,6 +68,34 @@ def test_determinism_and_permutation_invariance(lv, full):
     loc.close()
 
 
+def test_neighbour_reuse_and_graph_replay_change_nothing(lv, full, monkeypatch):
+    """evaluations after the first reuse the stored neighbours where lv_reuse_kernel can vouch for them, and an
+    update is replayed as a CUDA graph: both must leave every number of the update bit-identical"""
+    def run(env):
+        for k in ("LV_NO_REUSE", "LV_NO_GRAPH"):
+            monkeypatch.delenv(k, raising=False)
+        for k in env:
+            monkeypatch.setenv(k, "1")
+        loc = lv.Localizer(full["prm"])                 # the switches are read by lv_create
+        loc.map_build(full["map"])
+        out = []
+        for k in range(2):
+            loc.set_state(full["x_props"][k], full["P0"])
+            st, x, P, logs = loc.correct(full["sweeps"][k])
+            out.append((st, x, P, logs))
+        loc.close()
+        return out
+    base = run(["LV_NO_REUSE", "LV_NO_GRAPH"])
+    for env in ([], ["LV_NO_GRAPH"], ["LV_NO_REUSE"]):
+        got = run(env)
+        for (st0, x0, P0, l0), (st1, x1, P1, l1) in zip(base, got):
+            assert st0 == st1 == 0 and len(l0) == len(l1)
+            assert (x0 == x1).all() and (P0 == P1).all()
+            for a, b in zip(l0, l1):
+                assert a["n_matches"] == b["n_matches"]
+                assert (a["HTH"] == b["HTH"]).all() and (a["HTh"] == b["HTh"]).all() and (a["dx"] == b["dx"]).all()
+
+
 def test_streaming_predict_correct_map_update(lv, O, full):
     """three sweeps of the sequence: IMU propagation, iterated update, Mapper::add with the 0.2 m rule.
 
