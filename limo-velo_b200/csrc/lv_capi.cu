@@ -57,6 +57,7 @@ struct lv_context {
     float4* d_ref = nullptr;           /* max_points: reuse reference (lv_reuse_kernel) */
     uint32_t* d_redo = nullptr;        /* max_points */
     bool use_reuse = true;
+    bool use_pdl = true;               /* programmatic dependent launch between the kernels of an update */
     double* d_reduced = nullptr;       /* 157 doubles */
     double* h_reduced = nullptr;       /* pinned */
     void* d_flush = nullptr;
@@ -232,6 +233,7 @@ lv_status lv_create(const lv_params* p, lv_handle* out) {
     LV_CUDA(cudaMalloc(&h->d_ref, sizeof(float4) * p->max_points));
     LV_CUDA(cudaMalloc(&h->d_redo, sizeof(uint32_t) * (p->max_points + 64)));   /* + one block of slack: read speculatively */
     h->use_reuse = getenv("LV_NO_REUSE") == nullptr;
+    h->use_pdl = getenv("LV_NO_PDL") == nullptr;
     LV_CUDA(cudaMalloc(&h->d_job, sizeof(MeasureJob)));
     measure_init();
     h->use_graph = getenv("LV_NO_GRAPH") == nullptr;
@@ -380,8 +382,8 @@ static lv_status upload_state(lv_context* h, const double* x, const double* P) {
 
 /* launch_measure() with one CUDA-event pair per kernel when profiling is on (never inside a capture) */
 static cudaError_t launch_measure_timed(lv_context* h, const MeasureArgs& a, int grid, int allow_events, int reuse,
-                                        int upd, int slot) {
-    if (!h->profile || !allow_events) return launch_measure(a, grid, h->stream, nullptr, reuse);
+                                        int upd, int slot, int pdl = 0) {
+    if (!h->profile || !allow_events) return launch_measure(a, grid, h->stream, nullptr, reuse, pdl);
     struct Ctx { lv_context* h; EventPair ep; bool on; int upd, slot; } ctx = {h, EventPair(), false, upd, slot};
     MeasureProbe probe;
     probe.ctx = &ctx;
@@ -394,7 +396,7 @@ static cudaError_t launch_measure_timed(lv_context* h, const MeasureArgs& a, int
             c->ep.upd = c->upd; c->ep.slot = c->slot;
         }
     };
-    return launch_measure(a, grid, h->stream, &probe, reuse);
+    return launch_measure(a, grid, h->stream, &probe, reuse, 0);   /* events between the kernels: no pdl */
 }
 
 /* ---- the update ------------------------------------------------------------------------------ */
@@ -474,7 +476,8 @@ static lv_status enqueue_update(lv_context* h, const float* d_xyz, int64_t n) {
     UpdateCtrl* c = h->d_ctrl;
     MeasureJob* job = h->d_job;
     int n32 = (int)n;
-    void* args[4] = {&c, &job, &d_xyz, &n32};
+    uint32_t* counters = h->d_hard_list + h->prm.max_points;
+    void* args[5] = {&c, &job, &d_xyz, &n32, &counters};
     cudaKernelNodeParams kp;
     memset(&kp, 0, sizeof(kp));
     kp.func = const_cast<void*>(ieskf_begin_kernel_ptr());
@@ -504,17 +507,19 @@ static lv_status enqueue_update(lv_context* h, const float* d_xyz, int64_t n) {
 }
 
 static lv_status enqueue_update_kernels(lv_context* h, const float* d_xyz, int64_t n, bool as_job) {
-    LV_CUDA(launch_ieskf_begin(h->d_ctrl, as_job ? h->d_job : nullptr, d_xyz, (int)n, h->stream));
+    const int pdl = (h->use_pdl && !h->profile) ? 1 : 0;
+    uint32_t* counters = h->d_hard_list + h->prm.max_points;
+    LV_CUDA(launch_ieskf_begin(h->d_ctrl, as_job ? h->d_job : nullptr, d_xyz, (int)n, counters, h->stream));
     if (!as_job) h->prof.total_launches += 1;
     MeasureArgs a = update_measure_args(h, d_xyz, n, as_job);
     const int grid = measure_grid((int)n);
     for (int e = 0; e <= h->prm.MAX_NUM_ITERS; ++e) {            /* i = -1 .. max_iter-1, esekfom.hpp:1634 */
         EventPair ep;
         bool pr;
-        LV_CUDA(launch_measure_timed(h, a, grid, as_job ? 0 : 1, e > 0, (int)(h->update_seq % kNevalsRing), e));
+        LV_CUDA(launch_measure_timed(h, a, grid, as_job ? 0 : 1, e > 0, (int)(h->update_seq % kNevalsRing), e, pdl));
         pr = prof_begin(h, 1, &ep);
         ep.upd = (int)(h->update_seq % kNevalsRing); ep.slot = e;
-        LV_CUDA(launch_ieskf_step(h->d_ctrl, h->iprm, h->d_partials, grid, h->stream));
+        LV_CUDA(launch_ieskf_step(h->d_ctrl, h->iprm, h->d_partials, grid, h->stream, pdl));
         if (pr) prof_end(h, &ep);
         if (!as_job) h->prof.total_launches += 4 + ((e > 0 && h->use_reuse) ? 1 : 0);
     }

@@ -97,8 +97,8 @@ struct MeasureProbe { void (*at)(void* ctx, int stage); void* ctx; };
 /* reuse != 0 (needs a.ref, evaluations after the first of an update): lv_reuse_kernel first, then the search only
  * over the queries it could not vouch for; the probe then sees stage 4 before the reuse kernel */
 cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st, const MeasureProbe* probe = nullptr,
-                           int reuse = 0);
-cudaError_t launch_ieskf_begin(UpdateCtrl* c, MeasureJob* job, const float* xyz, int n, cudaStream_t st);
+                           int reuse = 0, int pdl = 0);
+cudaError_t launch_ieskf_begin(UpdateCtrl* c, MeasureJob* job, const float* xyz, int n, uint32_t* counters, cudaStream_t st);
 const void* ieskf_begin_kernel_ptr();
 void measure_init();                          /* constant tables; call once before any capture           */
 /* the three kernels of launch_measure() (search instance, search-upper, fit) with their launch shapes, for
@@ -107,7 +107,7 @@ struct MeasureKernelShape { const void* func; unsigned grid, block; };
 enum { kMeasureKernels = 5 };   /* search, search-upper, fit, search over the redo list, reuse */
 void measure_kernel_shapes(const MeasureArgs& a, int grid, MeasureKernelShape out[kMeasureKernels]);
 cudaError_t launch_ieskf_step(UpdateCtrl* c, const IeskfParams& prm, const double* partials, int n_partials,
-                              cudaStream_t st);
+                              cudaStream_t st, int pdl = 0);
 /* stand-alone reduction of the partials (operator-boundary calls): out[0:144) HTH, [144:156) HTh, [156] Nm */
 cudaError_t launch_reduce_partials(const double* partials, int n_partials, double* out, cudaStream_t st);
 cudaError_t launch_set_frame(UpdateCtrl* c, cudaStream_t st);   /* frame from c->x, done = 0 */

@@ -19,6 +19,7 @@
  * 5 x 12 B neighbours), no tensor-core-shaped work.
  */
 #include <stdlib.h>
+#include <string.h>
 
 #ifdef LV_STEP_TIMING   /* tuning build only: per-phase clocks of the step kernel */
 __device__ long long g_step_clk[64];
@@ -49,6 +50,14 @@ static void init_pairs() {
     cudaMemcpyToSymbol(c_pair_b, b, sizeof(b));
     g_pairs_ready = true;
 }
+
+/* Programmatic dependent launch: every kernel of an update lets its successor's blocks be scheduled early
+ * (pdl_trigger) and waits for its predecessor's results (pdl_wait) only after a prologue that touches nothing
+ * the predecessor writes.  Every path through a kernel executes pdl_wait() and triggers only AFTER it, so
+ * "this kernel runs past its wait" implies "its predecessor is complete", and a prologue may read whatever
+ * was written two or more kernels ago.  Without the launch attribute both are no-ops. */
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 /* the sweep of this launch: kernel arguments, or the device-side job of a graph replay */
 struct JobView { const float* xyz; int n; int n_tiles; };
@@ -95,6 +104,8 @@ __device__ __forceinline__ void store_ref(const MeasureArgs& a, int qi, const fl
 template <int G, bool LIST>
 __global__ void __launch_bounds__(LV_SEARCH_THREADS) lv_search_kernel(const MeasureArgs a) {
     typedef GroupLanes<G> Grp;
+    pdl_wait();
+    pdl_trigger();                 /* the predecessor (begin / step / reuse kernel) writes the frame and the lists */
     /* the search is a chain of dependent round trips (flags -> point -> slot -> bucket): everything that does
      * not depend on an earlier answer is requested up front, the `done` test included */
     const int done = a.ctrl->done;                      /* update already finished (uniform over the grid) */
@@ -137,6 +148,8 @@ __global__ void __launch_bounds__(LV_SEARCH_THREADS) lv_search_kernel(const Meas
  * the redo list and through the search kernels as usual.  Results are identical either way.
  */
 __global__ void __launch_bounds__(128) lv_reuse_kernel(const MeasureArgs a) {
+    pdl_wait();
+    pdl_trigger();                 /* the step kernel before us writes the frame */
     if (a.ctrl->done) return;
     const JobView jb = job_view(a);
     const int qi = (int)(blockIdx.x * blockDim.x + threadIdx.x);
@@ -186,6 +199,8 @@ __global__ void __launch_bounds__(128) lv_reuse_kernel(const MeasureArgs a) {
  */
 template <int G>
 __global__ void __launch_bounds__(LV_SEARCH_THREADS) lv_search_persistent_kernel(const MeasureArgs a) {
+    pdl_wait();
+    pdl_trigger();
     if (a.ctrl->done) return;
     typedef GroupLanes<G> Grp;
     const JobView jb = job_view(a);
@@ -223,10 +238,15 @@ __global__ void __launch_bounds__(LV_SEARCH_THREADS) lv_search_persistent_kernel
  * length lives on the device; a fixed grid strides over it, so no host round trip is needed.
  */
 __global__ void __launch_bounds__(128) lv_search_upper_kernel(const MeasureArgs a) {
-    if (a.ctrl->done) return;
-    const uint32_t n_hard = *a.hard_count;
+    /* flags, frame and job were written two or more kernels ago: safe to fetch while the search still runs
+     * (a kernel triggers its successor only after its own wait, so "two kernels ago" is complete by now) */
+    const int done = a.ctrl->done;
     const JobView jb = job_view(a);
-    const Rt32& T = a.ctrl->frame.lidar_to_world;
+    const Rt32 T = a.ctrl->frame.lidar_to_world;
+    pdl_wait();                 /* the search kernel's work list and uncertified answers */
+    pdl_trigger();
+    if (done) return;
+    const uint32_t n_hard = *a.hard_count;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t h = warp; h < n_hard; h += n_warps) {
         const int qi = (int)a.hard_list[h];
@@ -257,13 +277,18 @@ __device__ __noinline__ void prepare_block(UpdateCtrl* c) {
 }
 
 __global__ void __launch_bounds__(kMeasureThreads, 4) lv_fit_kernel(const MeasureArgs a) {
-    if (a.ctrl->done) return;
+    /* prologue on data written two or more kernels ago (flags, frame, iterate): runs while the searches finish */
+    const int done = a.ctrl->done;
     /* with a.prep the grid has one extra block in front; it is dispatched first and is done long before
      * the measurement blocks, so the iterate-only algebra costs the update no time of its own */
     const int n_blocks = a.prep ? (int)gridDim.x - 1 : (int)gridDim.x;
     const int bid = a.prep ? (int)blockIdx.x - 1 : (int)blockIdx.x;
     if (bid < 0) {
-        prepare_block(a.prep);
+        if (!done) prepare_block(a.prep);
+        pdl_wait();
+        pdl_trigger();
+        /* the searches of this evaluation are over: reset their counters for the next one */
+        if (threadIdx.x < 3) a.hard_count[threadIdx.x] = 0u;
         return;
     }
 
@@ -276,6 +301,9 @@ __global__ void __launch_bounds__(kMeasureThreads, 4) lv_fit_kernel(const Measur
         for (int i = threadIdx.x; i < (int)(sizeof(Frame) / 4); i += kMeasureThreads) dst[i] = src[i];
     }
     __syncthreads();
+    pdl_wait();                 /* the neighbour lists */
+    pdl_trigger();
+    if (done) return;
 
     const int tid = threadIdx.x;
     const JobView jb = job_view(a);
@@ -409,6 +437,8 @@ __device__ void reduce_partials_block(const double* partials, int n_partials, do
 
 __global__ void __launch_bounds__(kStepThreads) lv_ieskf_step_kernel(UpdateCtrl* c, const IeskfParams prm,
                                                                      const double* partials, int n_partials) {
+    pdl_wait();
+    pdl_trigger();                 /* partials and the prepared P_j / dx_new of the fit kernel */
     if (c->done) return;
     __shared__ IeskfWork w;
     __shared__ double s_tmp[(kStepThreads / 32) * 96];
@@ -452,7 +482,10 @@ __global__ void __launch_bounds__(kStepThreads) lv_reduce_partials_kernel(const 
     if (threadIdx.x == 0) out[156] = (double)nm;
 }
 
-__global__ void __launch_bounds__(256) lv_ieskf_begin_kernel(UpdateCtrl* c, MeasureJob* job, const float* xyz, int n) {
+__global__ void __launch_bounds__(256) lv_ieskf_begin_kernel(UpdateCtrl* c, MeasureJob* job, const float* xyz, int n,
+                                                             uint32_t* counters) {
+    pdl_trigger();
+    if (counters && threadIdx.x < 3) counters[threadIdx.x] = 0u;    /* work-list lengths of the measurement kernels */
     if (job && threadIdx.x == 0) {
         job->xyz = xyz;
         job->n = n;
@@ -512,49 +545,66 @@ void measure_kernel_shapes(const MeasureArgs& a, int grid, MeasureKernelShape ou
     out[4].func = (const void*)lv_reuse_kernel; out[4].grid = (unsigned)((a.n + 127) / 128 > 0 ? (a.n + 127) / 128 : 1); out[4].block = 128;
 }
 
+/* <<<>>> with the programmatic-dependent-launch attribute when `pdl` (see pdl_wait above) */
+template <class... Params, class... Args>
+static cudaError_t launch_k(void (*kernel)(Params...), unsigned grid, unsigned block, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = pdl ? at : nullptr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, Params(args)...);
+}
+
 template <bool LIST>
-static void launch_search(const MeasureArgs& a, int group, int sgrid, cudaStream_t st) {
+static void launch_search(const MeasureArgs& a, int group, int sgrid, cudaStream_t st, bool pdl) {
     switch (group) {
-        case 1: lv_search_kernel<1, LIST><<<sgrid, LV_SEARCH_THREADS, 0, st>>>(a); break;
-        case 2: lv_search_kernel<2, LIST><<<sgrid, LV_SEARCH_THREADS, 0, st>>>(a); break;
-        case 8: lv_search_kernel<8, LIST><<<sgrid, LV_SEARCH_THREADS, 0, st>>>(a); break;
-        default: lv_search_kernel<4, LIST><<<sgrid, LV_SEARCH_THREADS, 0, st>>>(a); break;
+        case 1: launch_k(lv_search_kernel<1, LIST>, sgrid, LV_SEARCH_THREADS, st, pdl, a); break;
+        case 2: launch_k(lv_search_kernel<2, LIST>, sgrid, LV_SEARCH_THREADS, st, pdl, a); break;
+        case 8: launch_k(lv_search_kernel<8, LIST>, sgrid, LV_SEARCH_THREADS, st, pdl, a); break;
+        default: launch_k(lv_search_kernel<4, LIST>, sgrid, LV_SEARCH_THREADS, st, pdl, a); break;
     }
 }
 
-cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st, const MeasureProbe* probe, int reuse) {
+cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st, const MeasureProbe* probe, int reuse, int pdl) {
     init_pairs();
     const int group = search_group();
     const int sgrid = search_grid(a, group);
-    /* work-list length, the persistent search's cursor, redo-list length */
-    cudaMemsetAsync(a.hard_count, 0, 3 * sizeof(uint32_t), st);
+    /* work-list length, the persistent search's cursor, redo-list length; inside an update with pdl the kernels
+     * reset them themselves (begin kernel, fit kernel) so that every node of the update is a kernel */
+    if (!pdl) cudaMemsetAsync(a.hard_count, 0, 3 * sizeof(uint32_t), st);
     static const bool persist = getenv("LV_SEARCH_PERSIST") != nullptr;
     if (reuse && a.ref) {
         if (probe) probe->at(probe->ctx, 4);
-        lv_reuse_kernel<<<(a.n + 127) / 128 > 0 ? (a.n + 127) / 128 : 1, 128, 0, st>>>(a);
+        launch_k(lv_reuse_kernel, (a.n + 127) / 128 > 0 ? (a.n + 127) / 128 : 1, 128, st, pdl != 0, a);
         if (probe) probe->at(probe->ctx, 0);
-        launch_search<true>(a, group, sgrid, st);
+        launch_search<true>(a, group, sgrid, st, pdl != 0);
     } else {
         if (probe) probe->at(probe->ctx, 0);
-        if (persist) lv_search_persistent_kernel<4><<<148 * 12, LV_SEARCH_THREADS, 0, st>>>(a);
-        else launch_search<false>(a, group, sgrid, st);
+        if (persist) launch_k(lv_search_persistent_kernel<4>, 148 * 12, LV_SEARCH_THREADS, st, pdl != 0, a);
+        else launch_search<false>(a, group, sgrid, st, pdl != 0);
     }
     if (probe) probe->at(probe->ctx, 1);
-    lv_search_upper_kernel<<<148 * 8, 128, 0, st>>>(a);
+    launch_k(lv_search_upper_kernel, 148 * 8, 128, st, pdl != 0, a);
     if (probe) probe->at(probe->ctx, 2);
-    lv_fit_kernel<<<grid + (a.prep ? 1 : 0), kMeasureThreads, 0, st>>>(a);
+    launch_k(lv_fit_kernel, grid + (a.prep ? 1 : 0), kMeasureThreads, st, pdl != 0, a);
     if (probe) probe->at(probe->ctx, 3);
     return cudaGetLastError();
 }
-cudaError_t launch_ieskf_begin(UpdateCtrl* c, MeasureJob* job, const float* xyz, int n, cudaStream_t st) {
-    lv_ieskf_begin_kernel<<<1, 256, 0, st>>>(c, job, xyz, n);
+cudaError_t launch_ieskf_begin(UpdateCtrl* c, MeasureJob* job, const float* xyz, int n, uint32_t* counters, cudaStream_t st) {
+    lv_ieskf_begin_kernel<<<1, 256, 0, st>>>(c, job, xyz, n, counters);
     return cudaGetLastError();
 }
 const void* ieskf_begin_kernel_ptr() { return (const void*)lv_ieskf_begin_kernel; }
 cudaError_t launch_ieskf_step(UpdateCtrl* c, const IeskfParams& prm, const double* partials, int n_partials,
-                              cudaStream_t st) {
+                              cudaStream_t st, int pdl) {
     init_pairs();
-    lv_ieskf_step_kernel<<<1, kStepThreads, 0, st>>>(c, prm, partials, n_partials);
+    launch_k(lv_ieskf_step_kernel, 1, kStepThreads, st, pdl != 0, c, prm, partials, n_partials);
     return cudaGetLastError();
 }
 cudaError_t launch_reduce_partials(const double* partials, int n_partials, double* out, cudaStream_t st) {

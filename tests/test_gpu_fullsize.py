@@ -69,10 +69,11 @@ def test_determinism_and_permutation_invariance(lv, full):
 
 
 def test_neighbour_reuse_and_graph_replay_change_nothing(lv, full, monkeypatch):
-    """evaluations after the first reuse the stored neighbours where lv_reuse_kernel can vouch for them, and an
-    update is replayed as a CUDA graph: both must leave every number of the update bit-identical"""
+    """evaluations after the first reuse the stored neighbours where lv_reuse_kernel can vouch for them, an update is
+    replayed as a CUDA graph, its kernels overlap their launches (programmatic dependent launch): none of it may
+    change a single bit of the update"""
     def run(env):
-        for k in ("LV_NO_REUSE", "LV_NO_GRAPH"):
+        for k in ("LV_NO_REUSE", "LV_NO_GRAPH", "LV_NO_PDL"):
             monkeypatch.delenv(k, raising=False)
         for k in env:
             monkeypatch.setenv(k, "1")
@@ -85,8 +86,8 @@ def test_neighbour_reuse_and_graph_replay_change_nothing(lv, full, monkeypatch):
             out.append((st, x, P, logs))
         loc.close()
         return out
-    base = run(["LV_NO_REUSE", "LV_NO_GRAPH"])
-    for env in ([], ["LV_NO_GRAPH"], ["LV_NO_REUSE"]):
+    base = run(["LV_NO_REUSE", "LV_NO_GRAPH", "LV_NO_PDL"])
+    for env in ([], ["LV_NO_GRAPH"], ["LV_NO_REUSE"], ["LV_NO_PDL"], ["LV_NO_GRAPH", "LV_NO_PDL"]):
         got = run(env)
         for (st0, x0, P0, l0), (st1, x1, P1, l1) in zip(base, got):
             assert st0 == st1 == 0 and len(l0) == len(l1)
