@@ -53,7 +53,7 @@ struct lv_context {
     double* d_partials = nullptr;
     int4* d_nn_a = nullptr;            /* max_points: K1 -> K2 hand-over */
     int2* d_nn_b = nullptr;
-    uint32_t* d_hard_list = nullptr;   /* max_points + 3: work list of K1b, its length, search cursor, redo length */
+    uint32_t* d_hard_list = nullptr;   /* max_points + 3: work list of K1b, its length, a spare word, redo length */
     float4* d_ref = nullptr;           /* max_points: reuse reference (lv_reuse_kernel) */
     uint32_t* d_redo = nullptr;        /* max_points */
     bool use_reuse = true;

@@ -48,7 +48,7 @@ struct MeasureArgs {
     int4* nn_a;                /* n: search result handed from K1 to K2 (neighbours 0..3)      */
     int2* nn_b;                /* n: (neighbour 4, bits of the 5th squared distance)         */
     uint32_t* hard_list;       /* n: queries level 0 could not certify (K1 -> K1b)           */
-    uint32_t* hard_count;      /* [0] length of hard_list, [1] cursor of the persistent search, [2] length of redo_list */
+    uint32_t* hard_count;      /* [0] length of hard_list, [1] spare, [2] length of redo_list */
     /* reuse of neighbours across the evaluations of one update (NULL: off) */
     float4* ref;               /* n: world position the stored neighbours were searched from + outsider bound */
     uint32_t* redo_list;       /* n: queries whose neighbours could not be reused (Kv -> K1)  */

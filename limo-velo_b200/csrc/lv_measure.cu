@@ -104,8 +104,8 @@ __device__ __forceinline__ void store_ref(const MeasureArgs& a, int qi, const fl
 template <int G, bool LIST>
 __global__ void __launch_bounds__(LV_SEARCH_THREADS) lv_search_kernel(const MeasureArgs a) {
     typedef GroupLanes<G> Grp;
-    pdl_wait();
-    pdl_trigger();                 /* the predecessor (begin / step / reuse kernel) writes the frame and the lists */
+    pdl_wait();                 /* the predecessor (begin / step / reuse kernel) writes the frame and the lists */
+    pdl_trigger();
     /* the search is a chain of dependent round trips (flags -> point -> slot -> bucket): everything that does
      * not depend on an earlier answer is requested up front, the `done` test included */
     const int done = a.ctrl->done;                      /* update already finished (uniform over the grid) */
@@ -148,37 +148,48 @@ __global__ void __launch_bounds__(LV_SEARCH_THREADS) lv_search_kernel(const Meas
  * the redo list and through the search kernels as usual.  Results are identical either way.
  */
 __global__ void __launch_bounds__(128) lv_reuse_kernel(const MeasureArgs a) {
-    pdl_wait();
-    pdl_trigger();                 /* the step kernel before us writes the frame */
-    if (a.ctrl->done) return;
+    /* Before the wait: everything but the new frame.  The sweep, the stored neighbours (written by the previous
+     * evaluation's search kernels, three or more kernels ago) and the map are fetched while the step kernel
+     * still runs; after the wait only the frame is missing. */
     const JobView jb = job_view(a);
     const int qi = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-    bool redo = false;
-    if (qi < jb.n) {
-        const Rt32& T = a.ctrl->frame.lidar_to_world;
-        float g[3];
-        rt_apply(T, jb.xyz[3 * qi], jb.xyz[3 * qi + 1], jb.xyz[3 * qi + 2], g);
+    const bool have = qi < jb.n;
+    float p[3] = {0.f, 0.f, 0.f}, q[5][3];
+    float ref[4] = {0.f, 0.f, 0.f, 0.f};
+    int id[5] = {-1, -1, -1, -1, -1};
+    bool general = false, cand = false;
+    if (have) {
+        p[0] = jb.xyz[3 * qi]; p[1] = jb.xyz[3 * qi + 1]; p[2] = jb.xyz[3 * qi + 2];
         const float4 r4 = a.ref[qi];
         const int4 na = a.nn_a[qi];
         const int2 nb = a.nn_b[qi];
-        redo = true;
-        if (r4.w > 0.f && nb.x != -1) {
-            const bool general = nb.x < -1;      /* positions in pts[] (stored as -2 - p) or in halo[] */
+        ref[0] = r4.x; ref[1] = r4.y; ref[2] = r4.z; ref[3] = r4.w;
+        cand = r4.w > 0.f && nb.x != -1;
+        if (cand) {
+            general = nb.x < -1;                 /* positions in pts[] (stored as -2 - p) or in halo[] */
             const float4* src = general ? a.map.pts : a.map.halo;
-            int id[5] = {na.x, na.y, na.z, na.w, nb.x};
-            float q[5][3];
+            id[0] = na.x; id[1] = na.y; id[2] = na.z; id[3] = na.w; id[4] = nb.x;
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
                 id[k] = general ? -2 - id[k] : id[k];
-                const float4 p = load_point(src + id[k]);
-                q[k][0] = p.x; q[k][1] = p.y; q[k][2] = p.z;
+                const float4 v = load_point(src + id[k]);
+                q[k][0] = v.x; q[k][1] = v.y; q[k][2] = v.z;
             }
-            const float ref[4] = {r4.x, r4.y, r4.z, r4.w};
-            Top5 t;
-            if (query_reusable(ref, g, q, id, a.max_d2, t)) {
-                store_neighbours(a, qi, t, general);
-                redo = false;
-            }
+        }
+    }
+    pdl_wait();                 /* the step kernel before us writes the frame and the done flag */
+    pdl_trigger();
+    if (a.ctrl->done) return;
+    bool redo = false;
+    if (have) {
+        const Rt32& T = a.ctrl->frame.lidar_to_world;
+        float g[3];
+        rt_apply(T, p[0], p[1], p[2], g);
+        redo = true;
+        Top5 t;
+        if (cand && query_reusable(ref, g, q, id, a.max_d2, t)) {
+            store_neighbours(a, qi, t, general);
+            redo = false;
         }
     }
     /* one atomic per warp */
@@ -189,47 +200,6 @@ __global__ void __launch_bounds__(128) lv_reuse_kernel(const MeasureArgs a) {
         if (lane == leader) base = atomicAdd(a.hard_count + 2, (uint32_t)__popc(m));
         base = __shfl_sync(0xffffffffu, base, leader);
         if (redo) a.redo_list[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = (uint32_t)qi;
-    }
-}
-
-/*
- * K1, persistent form: 148 x 12 resident blocks, every warp draws batches of 32 / G queries from a device
- * counter until the sweep is exhausted.  Balances the SMs to within one batch instead of one block wave
- * (the plain grid is 1.15 waves of 12 blocks per SM: ncu r1 shows SMs active 26 k .. 52 k cycles of 59 k).
- */
-template <int G>
-__global__ void __launch_bounds__(LV_SEARCH_THREADS) lv_search_persistent_kernel(const MeasureArgs a) {
-    pdl_wait();
-    pdl_trigger();
-    if (a.ctrl->done) return;
-    typedef GroupLanes<G> Grp;
-    const JobView jb = job_view(a);
-    const Rt32& T = a.ctrl->frame.lidar_to_world;
-    const int lane = threadIdx.x & 31;
-    uint32_t* counter = a.hard_count + 1;
-    for (;;) {
-        int base = 0;
-        if (lane == 0) base = (int)atomicAdd(counter, 32u / G);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= jb.n) break;
-        const int qi = base + lane / G;
-        const bool have = qi < jb.n;
-        float g[3] = {0.f, 0.f, 0.f};
-        uint32_t bs = 0, bc = 0;
-        int st = 0;
-        if (have) {
-            rt_apply(T, jb.xyz[3 * qi], jb.xyz[3 * qi + 1], jb.xyz[3 * qi + 2], g);
-            const bool finite = (fabsf(g[0]) < 1e9f) && (fabsf(g[1]) < 1e9f) && (fabsf(g[2]) < 1e9f);
-            if (finite) st = level0_probe(a.map, g[0], g[1], g[2], &bs, &bc) ? 1 : 2;
-        }
-        Top5 t;
-        float region = 0.f;
-        const bool settled = level0_scan<Grp>(a.map, g[0], g[1], g[2], a.max_d2, bs, bc, st == 1, t, &region);
-        if (have && (lane & (G - 1)) == 0) {
-            store_neighbours(a, qi, t, false);
-            store_ref(a, qi, g, (st == 1 && settled) ? outsider_bound(t.d5, region) : 0.f);
-            if (st == 2 || (st == 1 && !settled)) a.hard_list[atomicAdd(a.hard_count, 1u)] = (uint32_t)qi;
-        }
     }
 }
 
@@ -437,25 +407,27 @@ __device__ void reduce_partials_block(const double* partials, int n_partials, do
 
 __global__ void __launch_bounds__(kStepThreads) lv_ieskf_step_kernel(UpdateCtrl* c, const IeskfParams prm,
                                                                      const double* partials, int n_partials) {
-    pdl_wait();
-    pdl_trigger();                 /* partials and the prepared P_j / dx_new of the fit kernel */
-    if (c->done) return;
+    /* before the wait: what the previous step (or begin) kernel left, two or more kernels ago */
+    static_assert(kStepThreads >= 99 && 2 * kStepThreads >= kN * kN, "one pass for the state, two for P_j");
+    const int t = threadIdx.x;
+    const int done = c->done;
+    double sv = 0.0;
+    if (t < 26) sv = c->x[t];
+    else if (t < 52) sv = c->x_prop[t - 26];
+    int cv = 0;
+    if (t >= 96 && t < 99) cv = t == 96 ? c->n_evals : (t == 97 ? c->t : c->iter);
+    pdl_wait();                 /* partials and the prepared P_j / dx_new of the fit kernel */
+    pdl_trigger();
+    if (done) return;
     __shared__ IeskfWork w;
     __shared__ double s_tmp[(kStepThreads / 32) * 96];
     ExecBlock ex;
     LV_CK(0);
     /* ieskf_load(), split: the loads are issued here and parked in shared memory after the reduction, so
      * they are in flight together with the partials */
-    static_assert(kStepThreads >= 75 && 2 * kStepThreads >= kN * kN, "one pass for the state, two for P_j");
-    const int t = threadIdx.x;
     const double pj0 = t < kN * kN ? c->P_j[t] : 0.0;
     const double pj1 = t + kStepThreads < kN * kN ? c->P_j[t + kStepThreads] : 0.0;
-    double sv = 0.0;
-    if (t < 26) sv = c->x[t];
-    else if (t < 52) sv = c->x_prop[t - 26];
-    else if (t < 75) sv = c->dx_new[t - 52];
-    int cv = 0;
-    if (t >= 96 && t < 99) cv = t == 96 ? c->n_evals : (t == 97 ? c->t : c->iter);
+    if (t >= 52 && t < 75) sv = c->dx_new[t - 52];
     LV_CK(1);
     reduce_partials_block(partials, n_partials, s_tmp, w.HTH, w.HTh, &w.n_matches);
     if (t < kN * kN) w.P[t] = pj0;
@@ -575,10 +547,9 @@ cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st, cons
     init_pairs();
     const int group = search_group();
     const int sgrid = search_grid(a, group);
-    /* work-list length, the persistent search's cursor, redo-list length; inside an update with pdl the kernels
+    /* work-list length, a spare word, redo-list length; inside an update with pdl the kernels
      * reset them themselves (begin kernel, fit kernel) so that every node of the update is a kernel */
     if (!pdl) cudaMemsetAsync(a.hard_count, 0, 3 * sizeof(uint32_t), st);
-    static const bool persist = getenv("LV_SEARCH_PERSIST") != nullptr;
     if (reuse && a.ref) {
         if (probe) probe->at(probe->ctx, 4);
         launch_k(lv_reuse_kernel, (a.n + 127) / 128 > 0 ? (a.n + 127) / 128 : 1, 128, st, pdl != 0, a);
@@ -586,8 +557,7 @@ cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st, cons
         launch_search<true>(a, group, sgrid, st, pdl != 0);
     } else {
         if (probe) probe->at(probe->ctx, 0);
-        if (persist) launch_k(lv_search_persistent_kernel<4>, 148 * 12, LV_SEARCH_THREADS, st, pdl != 0, a);
-        else launch_search<false>(a, group, sgrid, st, pdl != 0);
+        launch_search<false>(a, group, sgrid, st, pdl != 0);
     }
     if (probe) probe->at(probe->ctx, 1);
     launch_k(lv_search_upper_kernel, 148 * 8, 128, st, pdl != 0, a);
