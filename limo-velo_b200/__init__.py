@@ -305,6 +305,19 @@ class Localizer:
                     allow=(EMPTY_MAP, TOO_FEW_MATCHES))
         return st, x, P, _logs_to_py(logs, ne.value)
 
+    def correct_buffers(self):
+        """preallocated outputs for correct_raw (benchmarks: keeps numpy / ctypes construction out of the timed call)"""
+        return dict(logs=(IterLog * MAX_EVALS)(), ne=C.c_int32(0), x=np.zeros(STATE_LEN), P=np.zeros((DOF, DOF)))
+
+    def correct_raw(self, raw_ptr, n, buf, time=0.0):
+        """lv_correct on a host pointer, nothing else: returns the status; unpack `buf` with correct_unpack"""
+        return self.L.lv_correct(self.h, C.cast(raw_ptr, C.POINTER(C.c_float)), n, float(time), buf["logs"],
+                                 C.byref(buf["ne"]), _d(buf["x"]), _d(buf["P"]))
+
+    @staticmethod
+    def correct_unpack(buf):
+        return buf["x"].copy(), buf["P"].copy(), _logs_to_py(buf["logs"], buf["ne"].value)
+
     def correct_device(self, d_ptr, n, time=0.0):
         return _check(self.L.lv_correct_device(self.h, d_ptr, n, float(time)), allow=(EMPTY_MAP,))
 

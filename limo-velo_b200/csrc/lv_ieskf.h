@@ -86,7 +86,6 @@ struct IeskfWork {
     double J[3][9];           /* J blocks: SO3@3, SO3@6 (3x3), S2@21 (2x2 in the first 4) */
     double L[kN * kN];
     double xn[kStateLen];     /* x [+] dx_ while x is still needed                        */
-    Rt32 X, IL;               /* fp32 pose / extrinsics of xn (make_frame's two halves)   */
     double pivval;
     int64_t n_matches;
     int32_t piv;
@@ -522,21 +521,22 @@ LV_HD_NOINLINE void ieskf_step(Ex& ex, const IeskfParams& prm, UpdateCtrl* c, Ie
     LV_PAR(i, 12) lg->HTh[i] = w->HTh[i];
     LV_PAR(i, n) lg->dx[i] = w->dxs[i];
     LV_TK(24 + (ex.tid >> 5));
-    if (ex.is_task(0)) {   /* pose: pos, rot  ->  X = (R, t) in fp32 (State.cpp:51-62), R^-1 */
+    if (ex.is_task(0)) {   /* pose and extrinsics -> the frame of the next measurement (make_frame, State.cpp:51-62) */
         for (int i = 0; i < 3; ++i) w->xn[kPos + i] = w->x[kPos + i] + w->dnd[i];
-        const Quatd q = quat_mul(load_quat(w->x + kRot), so3_exp(load_vec3(w->dnd + 3), 0.5));
-        store_quat(w->xn + kRot, q);
-        const Mat3d R = quat_to_rot(q), Ri = quat_to_rot(quat_conj(q));
-        for (int i = 0; i < 9; ++i) { w->X.R[i] = (float)R.m[i]; c->frame.R_inv[i] = Ri.m[i]; }
-        for (int i = 0; i < 3; ++i) w->X.t[i] = (float)w->xn[kPos + i];
-    }
-    if (ex.is_task(1)) {   /* extrinsics: offset_R_L_I, offset_T_L_I */
         for (int i = 0; i < 3; ++i) w->xn[kOffT + i] = w->x[kOffT + i] + w->dnd[9 + i];
-        const Quatd q = quat_mul(load_quat(w->x + kOffR), so3_exp(load_vec3(w->dnd + 6), 0.5));
-        store_quat(w->xn + kOffR, q);
+        const Quatd q = quat_mul(load_quat(w->x + kRot), so3_exp(load_vec3(w->dnd + 3), 0.5));
+        const Quatd ql = quat_mul(load_quat(w->x + kOffR), so3_exp(load_vec3(w->dnd + 6), 0.5));
+        store_quat(w->xn + kRot, q);
+        store_quat(w->xn + kOffR, ql);
         const Mat3d R = quat_to_rot(q), Ri = quat_to_rot(quat_conj(q));
-        for (int i = 0; i < 9; ++i) { w->IL.R[i] = (float)R.m[i]; c->frame.RLI_inv[i] = Ri.m[i]; }
-        for (int i = 0; i < 3; ++i) w->IL.t[i] = (float)w->xn[kOffT + i];
+        const Mat3d RL = quat_to_rot(ql), RLi = quat_to_rot(quat_conj(ql));
+        Rt32 X, IL;
+        for (int i = 0; i < 9; ++i) { X.R[i] = (float)R.m[i]; IL.R[i] = (float)RL.m[i]; }
+        for (int i = 0; i < 3; ++i) { X.t[i] = (float)w->xn[kPos + i]; IL.t[i] = (float)w->xn[kOffT + i]; }
+        for (int i = 0; i < 9; ++i) { c->frame.R_inv[i] = Ri.m[i]; c->frame.RLI_inv[i] = RLi.m[i]; }
+        c->frame.lidar_to_world = rt_mul(X, IL);
+        c->frame.world_to_lidar = rt_mul(rt_inv(IL), rt_inv(X));
+        c->frame.lidar_to_imu = IL;
     }
     if (ex.is_task(2)) store_vec3(w->xn + kGrav, s2_boxplus(load_vec3(w->x + kGrav), w->dnd[21], w->dnd[22]));
     if (ex.is_task(3)) {
@@ -563,10 +563,6 @@ LV_HD_NOINLINE void ieskf_step(Ex& ex, const IeskfParams& prm, UpdateCtrl* c, Ie
             make_frame(w->xn, &c->frame);
         }
         ex.sync();
-    } else if (ex.tid == 0 && !w->finish) {
-        c->frame.lidar_to_world = rt_mul(w->X, w->IL);
-        c->frame.world_to_lidar = rt_mul(rt_inv(w->IL), rt_inv(w->X));
-        c->frame.lidar_to_imu = w->IL;
     }
     if (ex.is_task(1)) lg->degenerate = w->degen;
     LV_PAR(i, kStateLen) {

@@ -271,12 +271,19 @@ __global__ void __launch_bounds__(kMeasureThreads, 4) lv_fit_kernel(const Measur
         for (int i = threadIdx.x; i < (int)(sizeof(Frame) / 4); i += kMeasureThreads) dst[i] = src[i];
     }
     __syncthreads();
+    const int tid = threadIdx.x;
+    const JobView jb = job_view(a);
+    /* the first tile's world points need only the sweep and the frame: transform them before the wait too */
+    float g0[3] = {0.f, 0.f, 0.f};
+    {
+        const int i = bid * kMeasureThreads + tid;
+        if (bid < jb.n_tiles && i < jb.n)
+            rt_apply(s_frame.lidar_to_world, jb.xyz[3 * i], jb.xyz[3 * i + 1], jb.xyz[3 * i + 2], g0);
+    }
     pdl_wait();                 /* the neighbour lists */
     pdl_trigger();
     if (done) return;
 
-    const int tid = threadIdx.x;
-    const JobView jb = job_view(a);
     double acc = 0.0;
     int count = 0;
 
@@ -285,8 +292,8 @@ __global__ void __launch_bounds__(kMeasureThreads, 4) lv_fit_kernel(const Measur
         bool chosen = false;
         double row[12], hval = 0.0;
         if (i < jb.n) {
-            float g[3];
-            rt_apply(s_frame.lidar_to_world, jb.xyz[3 * i], jb.xyz[3 * i + 1], jb.xyz[3 * i + 2], g);
+            float g[3] = {g0[0], g0[1], g0[2]};
+            if (tile != bid) rt_apply(s_frame.lidar_to_world, jb.xyz[3 * i], jb.xyz[3 * i + 1], jb.xyz[3 * i + 2], g);
             const int4 na = a.nn_a[i];
             const int2 nb = a.nn_b[i];
             const float d4 = __int_as_float(nb.y);
