@@ -302,6 +302,38 @@ def run_native(args, rank, local_rank, world_size):
         loc.synchronize()
         t_add.append(time.perf_counter() - t0)
 
+    # ---- deskew (Compensator::compensate), reported beside the headline ----
+    deskew = None
+    try:
+        dk = deskew_case(lv, world, prm, sweeps[0])
+        d_in, d_t = loc.upload(dk["xyz"]), loc.upload(dk["t"])
+        for _ in range(3):
+            loc.compensate_device(dk["path"], dk["xt2"], d_in, d_t, n, d_in)
+        reps = 50
+        loc.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            loc.compensate_device(dk["path"], dk["xt2"], d_in, d_t, n, d_in)      # blocking: path upload + 2 kernels + flag
+        dt_dev = (time.perf_counter() - t0) / reps
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            loc.compensate(dk["path"], dk["xt2"], dk["xyz"], dk["t"])                # host buffers: + H2D 20 B/pt, D2H 12 B/pt
+        dt_host = (time.perf_counter() - t0) / reps
+        loc.device_free(d_in); loc.device_free(d_t)
+        cpu_ms = None
+        if rank == 0 and not args.no_cpu:                           # the oracle's restatement, one host thread
+            O = G.load_oracle()
+            po = [O.State32.from_buffer_copy(s) for s in dk["path"]]
+            xo = O.State32.from_buffer_copy(dk["xt2"])
+            t0 = time.perf_counter()
+            O.compensate(po, xo, dk["xyz"], dk["t"])
+            cpu_ms = 1e3 * (time.perf_counter() - t0)
+        deskew = {"points": n, "path_states": len(dk["path"]), "lv_compensate_device_ms": 1e3 * dt_dev, "cpu_oracle_ms": cpu_ms,
+                  "lv_compensate_host_ms": 1e3 * dt_host, "points_per_s_device": n / dt_dev,
+                  "bytes_per_point": 32, "note": "blocking calls, wall clock; launch-bound at this size"}
+    except Exception as e:                                         # never let the side measurement break the headline
+        deskew = {"error": str(e)}
+
     # ---- max over ranks / totals ----
     tot = torch.tensor([step_ms, float(pts), float(matched), e2e_s, float(e2e_pts), float(launches)],
                        dtype=torch.float64, device="cuda")
@@ -368,6 +400,7 @@ def run_native(args, rank, local_rank, world_size):
                          "kernel": dominant, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_POINT * n},
             "cpu_baseline": cpu,
             "map_update": {"lv_map_add_ms": 1e3 * min(t_add), "points_added": n, "map_points": loc.map_size()},
+            "deskew": deskew,
             "final_position_error_m": pose_err,
             "clocks": clock_info,
         }
@@ -377,6 +410,24 @@ def run_native(args, rank, local_rank, world_size):
     loc.close()
     if world_size > 1:
         dist.destroy_process_group()
+
+
+def deskew_case(lv, world, prm, sweep, t1=10.0, t2=10.1, n_states=4, imu_hz=400.0):
+    """a 0.1 s sweep at 15 m/s: KF states every ~33 ms, IMU at 400 Hz, point stamps spread over the sweep"""
+    rng = np.random.default_rng(SEED + 77)
+    st_times = np.linspace(t1 - 0.012, t2 - 0.004, n_states)
+    imu_t = np.arange(st_times[0] + 0.2 / imu_hz, t2 + 1.5 / imu_hz, 1.0 / imu_hz)   # Compensator::path: from the first state on
+    imu_a = (np.array([0.3, -0.2, 9.8]) + rng.normal(0, 0.05, (len(imu_t), 3))).astype(np.float32)
+    imu_w = (np.array([0.02, -0.01, 0.3]) + rng.normal(0, 0.01, (len(imu_t), 3))).astype(np.float32)
+    states = []
+    for ts in st_times:
+        x = world.pose(15.0 + 15.0 * (ts - t1), prm).copy()
+        x[14:17] = [15.0, 0.3, -0.1]
+        j = int(np.searchsorted(imu_t, ts))
+        states.append(lv.state_from_ikfom(prm, x, ts, imu_a[j], imu_w[j]))
+    path = lv.compensator_upsample(states, imu_a, imu_w, imu_t)
+    return dict(path=path, xt2=lv.compensator_get_t2(path, t2), xyz=np.ascontiguousarray(sweep, np.float32),
+                t=np.linspace(t1, t2, len(sweep)))
 
 
 def world_points(sweep, x):

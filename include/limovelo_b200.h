@@ -187,6 +187,37 @@ lv_status lv_profile_enable(lv_handle h, int on);             /* CUDA-event timi
 lv_status lv_profile_get(lv_handle h, lv_profile* out, int reset);
 lv_status lv_flush_l2(lv_handle h);                           /* writes a 256 MiB scratch      */
 
+/* ---- Compensator boundary: deskew (include/Headers/Compensator.hpp, src/Modules/Compensator.cpp) ---- */
+/* `State` of include/Headers/Objects.hpp:97-120 (single precision like the reference), row-major matrices */
+typedef struct lv_state32 {
+    float R[9];
+    float pos[3], vel[3], bw[3], ba[3], g[3];
+    float RLI[9], tLI[3];
+    float a[3], w[3];          /* last controls (State.cpp:129-131) */
+    double time;
+} lv_state32;
+/* State(const state_ikfom&, double) (State.cpp:40-62): x = flat state (layout above); a, w = the IMU sample that
+ * follows `time` (Accumulator::get_next_imu); g = p->initial_gravity (State.cpp:21)                    */
+void lv_state_from_ikfom(const lv_params* p, const double* x, double time, const float a[3], const float w[3],
+                         lv_state32* out);
+/* State::operator+=(const IMU&) (State.cpp:73-75 -> update :122-132 -> propagate_f :103-120), host */
+void lv_state_add_imu(lv_state32* s, const float a[3], const float w[3], double time);
+/* Compensator::upsample (Compensator.cpp:73-113): states (before t1 .. t2) + IMU samples (a, w: ni x 3, t: ni) ->
+ * the integrated path; returns the number of states the path has (writes at most cap)                   */
+int32_t lv_compensator_upsample(const lv_state32* states, int32_t ns, const float* imu_a, const float* imu_w,
+                                const double* imu_t, int32_t ni, lv_state32* out, int32_t cap);
+/* Compensator::get_t2 (Compensator.cpp:55-63) */
+void lv_compensator_get_t2(const lv_state32* path, int32_t ns, double t2, lv_state32* out);
+/* Compensator::compensate(states, Xt2, points) (Compensator.cpp:123-146): every point is carried from the pose at
+ * its own timestamp to the LiDAR frame at t2.  xyz (n x 3) and t (n, ascending, inside [path[0].time,
+ * path[ns-1].time]) are HOST buffers; xyz_out (n x 3, host) receives the deskewed points in input order, which is
+ * what Localizator::correct takes.  LV_ERR_ARG if a timestamp lies outside the path (the reference asserts).   */
+lv_status lv_compensate(lv_handle h, const lv_state32* path, int32_t ns, const lv_state32* Xt2, const float* xyz,
+                        const double* t, int64_t n, float* xyz_out);
+/* same on device-resident buffers (lv_device_alloc); d_xyz_out may alias d_xyz                              */
+lv_status lv_compensate_device(lv_handle h, const lv_state32* path, int32_t ns, const lv_state32* Xt2,
+                               const float* d_xyz, const double* d_t, int64_t n, float* d_xyz_out);
+
 /* ---- synthetic reader (replaces the ROS subscribers of src/main.cpp:27-39) ---- */
 typedef struct lv_synth_world lv_synth_world;
 /* seeded "city-block" world whose surface sampling holds exactly m map points              */

@@ -185,6 +185,57 @@ def _logs_to_py(logs, n):
     return out
 
 
+class State32(C.Structure):
+    """lv_state32: `State` of the reference (Objects.hpp:97-120), single precision"""
+    _fields_ = [("R", C.c_float * 9), ("pos", C.c_float * 3), ("vel", C.c_float * 3), ("bw", C.c_float * 3),
+                ("ba", C.c_float * 3), ("g", C.c_float * 3), ("RLI", C.c_float * 9), ("tLI", C.c_float * 3),
+                ("a", C.c_float * 3), ("w", C.c_float * 3), ("time", C.c_double)]
+
+    def as_tuple(self):
+        return tuple(np.array(getattr(self, k)[:], dtype=np.float32).tobytes() for k, _ in self._fields_[:-1]) + (self.time,)
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(t) for t in v])
+
+
+def state_from_ikfom(params, x, time, a, w):
+    """State(const state_ikfom&, double) (State.cpp:40-62)"""
+    out = State32()
+    lib().lv_state_from_ikfom(C.byref(params), _d(np.ascontiguousarray(x, np.float64)), C.c_double(time), _f3(a), _f3(w),
+                              C.byref(out))
+    return out
+
+
+def state_add_imu(state, a, w, time):
+    """State::operator+=(IMU) on a copy"""
+    out = State32.from_buffer_copy(state)
+    lib().lv_state_add_imu(C.byref(out), _f3(a), _f3(w), C.c_double(time))
+    return out
+
+
+def compensator_upsample(states, imu_a, imu_w, imu_t):
+    """Compensator::upsample: list of State32 + IMU arrays -> the integrated path (list of State32)"""
+    ns, ni = len(states), len(imu_t)
+    arr = (State32 * ns)(*states)
+    a = np.ascontiguousarray(imu_a, np.float32).reshape(ni, 3)
+    w = np.ascontiguousarray(imu_w, np.float32).reshape(ni, 3)
+    t = np.ascontiguousarray(imu_t, np.float64)
+    cap = ns + ni + 8
+    out = (State32 * cap)()
+    lib().lv_compensator_upsample.restype = C.c_int32
+    n = lib().lv_compensator_upsample(arr, ns, _f(a), _f(w), _d(t), ni, out, cap)
+    assert n <= cap
+    return [State32.from_buffer_copy(out[i]) for i in range(n)]
+
+
+def compensator_get_t2(path, t2):
+    arr = (State32 * len(path))(*path)
+    out = State32()
+    lib().lv_compensator_get_t2(arr, len(path), C.c_double(t2), C.byref(out))
+    return out
+
+
 def init_state_host(params, q_imu=(0, 0, 0, 1)):
     """Localizator::init_IKFoM_state on the host (no GPU needed)."""
     x, P = np.zeros(STATE_LEN), np.zeros((DOF, DOF))
@@ -304,6 +355,20 @@ class Localizer:
         st = _check(self.L.lv_correct(self.h, ptr, n, float(time), logs, C.byref(ne), _d(x), _d(P)),
                     allow=(EMPTY_MAP, TOO_FEW_MATCHES))
         return st, x, P, _logs_to_py(logs, ne.value)
+
+    def compensate(self, path, Xt2, xyz, t):
+        """Compensator::compensate (deskew) on host buffers: returns the points in the LiDAR frame at t2"""
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        t = np.ascontiguousarray(t, np.float64)
+        out = np.empty_like(xyz)
+        arr = (State32 * len(path))(*path)
+        _check(self.L.lv_compensate(self.h, arr, len(path), C.byref(Xt2), _f(xyz), _d(t), C.c_int64(xyz.shape[0]), _f(out)))
+        return out
+
+    def compensate_device(self, path, Xt2, d_xyz, d_t, n, d_out):
+        arr = (State32 * len(path))(*path)
+        return _check(self.L.lv_compensate_device(self.h, arr, len(path), C.byref(Xt2), C.c_void_p(d_xyz), C.c_void_p(d_t),
+                                                  C.c_int64(n), C.c_void_p(d_out)))
 
     def correct_buffers(self):
         """preallocated outputs for correct_raw (benchmarks: keeps numpy / ctypes construction out of the timed call)"""

@@ -59,6 +59,13 @@ struct lv_context {
     uint32_t* d_redo = nullptr;        /* max_points */
     bool use_reuse = true;
     bool use_pdl = true;               /* programmatic dependent launch between the kernels of an update */
+    /* Compensator (deskew) staging: lazily allocated */
+    lv_state32* d_path = nullptr;      /* deskew_max_states() */
+    lv_state32* h_path = nullptr;      /* pinned */
+    double* d_times = nullptr;         /* max_points */
+    float* d_deskew_in = nullptr;      /* max_points x 3 */
+    int* d_bad = nullptr;
+    int* h_bad = nullptr;              /* pinned */
     double* d_reduced = nullptr;       /* 157 doubles */
     double* h_reduced = nullptr;       /* pinned */
     void* d_flush = nullptr;
@@ -262,6 +269,7 @@ void lv_destroy(lv_handle h) {
     for (auto& e : h->pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& u : h->graphs) { cudaGraphExecDestroy(u.exec); cudaGraphDestroy(u.graph); }
     cudaFree(h->d_job); cudaFree(h->d_ref); cudaFree(h->d_redo);
+    cudaFree(h->d_path); cudaFreeHost(h->h_path); cudaFree(h->d_times); cudaFree(h->d_deskew_in); cudaFree(h->d_bad); cudaFreeHost(h->h_bad);
     MapBuffers& m = h->map;
     cudaFree(m.xyz); cudaFree(m.xyz_alt); cudaFree(m.keys); cudaFree(m.keys_sorted); cudaFree(m.vals); cudaFree(m.vals_sorted);
     cudaFree(m.pts);
@@ -690,6 +698,61 @@ lv_status lv_memcpy_h2d(lv_handle h, void* dst, const void* src, int64_t bytes) 
     LV_CUDA(cudaStreamSynchronize(h->stream));
     return LV_OK;
 }
+/* ---- Compensator::compensate ------------------------------------------------------------------ */
+static lv_status deskew_common(lv_context* h, const lv_state32* path, int32_t ns, const lv_state32* Xt2,
+                               const float* d_xyz, const double* d_t, int64_t n, float* d_out) {
+    if (!h->d_path) {
+        LV_CUDA(cudaMalloc(&h->d_path, sizeof(lv_state32) * deskew_max_states()));
+        LV_CUDA(cudaMallocHost(&h->h_path, sizeof(lv_state32) * deskew_max_states()));
+        LV_CUDA(cudaMalloc(&h->d_bad, sizeof(int)));
+        LV_CUDA(cudaMallocHost(&h->h_bad, sizeof(int)));
+    }
+    memcpy(h->h_path, path, sizeof(lv_state32) * (size_t)ns);
+    LV_CUDA(cudaMemcpyAsync(h->d_path, h->h_path, sizeof(lv_state32) * (size_t)ns, cudaMemcpyHostToDevice, h->stream));
+    LV_CUDA(launch_deskew(h->d_path, ns, *Xt2, path[0].time, path[ns - 1].time, d_xyz, d_t, n, d_out, h->d_bad, h->stream));
+    LV_CUDA(cudaMemcpyAsync(h->h_bad, h->d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    h->prof.total_launches += 2;
+    return LV_OK;
+}
+static lv_status deskew_args_ok(lv_context* h, const lv_state32* path, int32_t ns, const lv_state32* Xt2, const void* a,
+                                const void* b, int64_t n, const void* c) {
+    if (!h || !path || !Xt2 || !a || !b || !c || n <= 0 || ns < 2) return LV_ERR_ARG;
+    if (ns > deskew_max_states()) { set_error("deskew path too long"); return LV_ERR_CAPACITY; }
+    if (n > h->prm.max_points) { set_error("sweep capacity exceeded"); return LV_ERR_CAPACITY; }
+    for (int32_t s = 1; s < ns; ++s)
+        if (!(path[s - 1].time <= path[s].time)) { set_error("deskew path not sorted by time"); return LV_ERR_ARG; }
+    return LV_OK;
+}
+lv_status lv_compensate_device(lv_handle h, const lv_state32* path, int32_t ns, const lv_state32* Xt2,
+                               const float* d_xyz, const double* d_t, int64_t n, float* d_xyz_out) {
+    lv_status s = deskew_args_ok(h, path, ns, Xt2, d_xyz, d_t, n, d_xyz_out);
+    if (s != LV_OK) return s;
+    LV_CUDA(cudaSetDevice(h->prm.device));
+    s = deskew_common(h, path, ns, Xt2, d_xyz, d_t, n, d_xyz_out);
+    if (s != LV_OK) return s;
+    LV_CUDA(cudaStreamSynchronize(h->stream));
+    if (*h->h_bad) { set_error("deskew: a timestamp lies outside the path or the points are not time-sorted"); return LV_ERR_ARG; }
+    return LV_OK;
+}
+lv_status lv_compensate(lv_handle h, const lv_state32* path, int32_t ns, const lv_state32* Xt2, const float* xyz,
+                        const double* t, int64_t n, float* xyz_out) {
+    lv_status s = deskew_args_ok(h, path, ns, Xt2, xyz, t, n, xyz_out);
+    if (s != LV_OK) return s;
+    LV_CUDA(cudaSetDevice(h->prm.device));
+    if (!h->d_times) {
+        LV_CUDA(cudaMalloc(&h->d_times, sizeof(double) * h->prm.max_points));
+        LV_CUDA(cudaMalloc(&h->d_deskew_in, sizeof(float) * 3 * h->prm.max_points));
+    }
+    LV_CUDA(cudaMemcpyAsync(h->d_deskew_in, xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
+    LV_CUDA(cudaMemcpyAsync(h->d_times, t, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
+    s = deskew_common(h, path, ns, Xt2, h->d_deskew_in, h->d_times, n, h->d_deskew_in);
+    if (s != LV_OK) return s;
+    LV_CUDA(cudaMemcpyAsync(xyz_out, h->d_deskew_in, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, h->stream));
+    LV_CUDA(cudaStreamSynchronize(h->stream));
+    if (*h->h_bad) { set_error("deskew: a timestamp lies outside the path or the points are not time-sorted"); return LV_ERR_ARG; }
+    return LV_OK;
+}
+
 lv_status lv_synchronize(lv_handle h) {
     if (!h) return LV_ERR_ARG;
     LV_CUDA(cudaSetDevice(h->prm.device));

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/limovelo_b200.h"
 #include "lv_ieskf.h"
 #include "lv_voxel_search.h"
 
@@ -112,6 +113,11 @@ cudaError_t launch_ieskf_step(UpdateCtrl* c, const IeskfParams& prm, const doubl
 cudaError_t launch_reduce_partials(const double* partials, int n_partials, double* out, cudaStream_t st);
 cudaError_t launch_set_frame(UpdateCtrl* c, cudaStream_t st);   /* frame from c->x, done = 0 */
 cudaError_t launch_l2_flush(void* buf, size_t bytes, cudaStream_t st);
+
+/* lv_deskew.cu: Compensator::compensate.  d_bad (one int) is set when a timestamp is out of range / out of order */
+int deskew_max_states();
+cudaError_t launch_deskew(const lv_state32* d_path, int ns, const lv_state32& Xt2, double t_lo, double t_hi,
+                          const float* d_xyz, const double* d_t, int64_t n, float* d_out, int* d_bad, cudaStream_t st);
 
 }  // namespace lv
 #endif

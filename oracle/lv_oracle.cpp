@@ -1460,3 +1460,132 @@ void lvo_last_timing(double* knn_s, double* total_s) { *knn_s = g_knn_s; *total_
 void lvo_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// Deskew: State arithmetic and Compensator (fp32).  PARITY UNPINNED: the reference's Compensator
+// needs ROS/PCL/Eigen and cannot be built here, and its tests hold no vectors for it; this follows the source
+// text line by line (summation order of 3-term products as in the fp32 geometry above).
+// ------------------------------------------------------------------------------------------
+namespace {
+// SO3Math::Exp<float, float> (Utils.hpp:28-54)
+void so3_exp_f(const float* av, float dt, float* E) {
+    const float n = sqrtf((av[0] * av[0] + av[1] * av[1]) + av[2] * av[2]);
+    for (int i = 0; i < 9; ++i) E[i] = (i % 4 == 0) ? 1.f : 0.f;
+    if (!((double)n > 0.0000001)) return;
+    const float r[3] = {av[0] / n, av[1] / n, av[2] / n};
+    const float K[9] = {0.f, -r[2], r[1], r[2], 0.f, -r[0], -r[1], r[0], 0.f};
+    const float ang = n * dt;
+    const float sn = sinf(ang), c1 = (float)(1.0 - (double)cosf(ang));
+    float cK[9], KK[9];
+    for (int i = 0; i < 9; ++i) cK[i] = c1 * K[i];
+    m3mul_f(cK, K, KK);
+    for (int i = 0; i < 9; ++i) E[i] = (E[i] + sn * K[i]) + KK[i];
+}
+// State::propagate_f (State.cpp:103-120)
+void propagate_f(lvo_state32* s, const float* a, const float* w, float dt) {
+    float wb[3], ab[3], E[9], Rn[9], Rab[3];
+    for (int i = 0; i < 3; ++i) { wb[i] = w[i] - s->bw[i]; ab[i] = a[i] - s->ba[i]; }
+    so3_exp_f(wb, dt, E);
+    m3mul_f(s->R, E, Rn);
+    m3vec_f(s->R, ab, Rab);
+    float vn[3], pn[3];
+    for (int i = 0; i < 3; ++i) {
+        const float acc = Rab[i] - s->g[i];
+        vn[i] = s->vel[i] + acc * dt;
+        pn[i] = s->pos[i] + (s->vel[i] * dt + ((0.5f * acc) * dt) * dt);
+    }
+    memcpy(s->R, Rn, sizeof(Rn));
+    for (int i = 0; i < 3; ++i) { s->vel[i] = vn[i]; s->pos[i] = pn[i]; }
+}
+}  // namespace
+
+extern "C" {
+
+void lvo_state_from_ikfom(const double* x, double time, const float a[3], const float w[3],
+                          const float initial_gravity[3], lvo_state32* out) {
+    memset(out, 0, sizeof(*out));
+    const State32 s = make_state32(x);
+    memcpy(out->R, s.X.R, sizeof(out->R));
+    memcpy(out->RLI, s.IL.R, sizeof(out->RLI));
+    for (int i = 0; i < 3; ++i) {
+        out->pos[i] = s.X.t[i];
+        out->tLI[i] = s.IL.t[i];
+        out->vel[i] = (float)x[S_VEL + i];
+        out->bw[i] = (float)x[S_BG + i];
+        out->ba[i] = (float)x[S_BA + i];
+        out->g[i] = initial_gravity[i];     /* State() reads Config.initial_gravity and nothing overwrites it */
+        out->a[i] = a[i];
+        out->w[i] = w[i];
+    }
+    out->time = time;
+}
+
+void lvo_state_add_imu(lvo_state32* s, const float a[3], const float w[3], double time) {
+    const float dt = (float)(time - s->time);       /* State.cpp:124 */
+    propagate_f(s, a, w, dt);
+    s->time = time;
+    for (int i = 0; i < 3; ++i) {                   /* State.cpp:130-131: (double)0.5 * float vector, cast to float */
+        s->a[i] = 0.5f * s->a[i] + 0.5f * a[i];
+        s->w[i] = 0.5f * s->w[i] + 0.5f * w[i];
+    }
+}
+
+int lvo_upsample(const lvo_state32* states, int ns, const float* imu_a, const float* imu_w, const double* imu_t, int ni,
+                 lvo_state32* out, int cap) {
+    int s = 0, u = 0, no = 0;
+    auto push = [&](const lvo_state32& v) { if (no < cap) out[no] = v; ++no; };
+    lvo_state32 cur = states[0];
+    while (s < ns - 1) {
+        push(states[s]);
+        while (u < ni && imu_t[u] < states[s + 1].time) {
+            lvo_state_add_imu(&cur, imu_a + 3 * u, imu_w + 3 * u, imu_t[u]);
+            ++u;
+            push(cur);
+        }
+        cur = states[s++];          /* Compensator.cpp:98: the state BEFORE the increment (reference quirk) */
+    }
+    if (u >= ni) u = ni - 1;
+    push(states[ns - 1]);
+    cur = states[ns - 1];
+    while (cur.time < imu_t[ni - 1] && u < ni) {
+        lvo_state_add_imu(&cur, imu_a + 3 * u, imu_w + 3 * u, imu_t[u]);
+        ++u;
+        push(cur);
+    }
+    return no;
+}
+
+void lvo_get_t2(const lvo_state32* states, int ns, double t2, lvo_state32* out) {
+    int s = ns - 1;
+    while (t2 < states[s].time) --s;
+    *out = states[s];
+    const float a[3] = {out->a[0], out->a[1], out->a[2]}, w[3] = {out->w[0], out->w[1], out->w[2]};
+    lvo_state_add_imu(out, a, w, t2);
+}
+
+int64_t lvo_compensate(const lvo_state32* states, int ns, const lvo_state32* Xt2, const float* xyz, const double* t,
+                       int64_t n, float* xyz_out) {
+    Rt32 X2, IL2;
+    memcpy(X2.R, Xt2->R, sizeof(X2.R)); memcpy(X2.t, Xt2->pos, sizeof(X2.t));
+    memcpy(IL2.R, Xt2->RLI, sizeof(IL2.R)); memcpy(IL2.t, Xt2->tLI, sizeof(IL2.t));
+    const Rt32 back = rt_mul(rt_inv(IL2), rt_inv(X2));          /* Xt2.I_Rt_L().inv() * Xt2.inv() */
+    int64_t p = 0, no = 0;
+    for (int s = 0; s < ns - 1; ++s) {
+        while (p < n && states[s].time <= t[p] && t[p] <= states[s + 1].time) {
+            lvo_state32 Xtp = states[s];
+            const float a[3] = {Xtp.a[0], Xtp.a[1], Xtp.a[2]}, w[3] = {Xtp.w[0], Xtp.w[1], Xtp.w[2]};
+            lvo_state_add_imu(&Xtp, a, w, t[p]);
+            Rt32 X, IL;
+            memcpy(X.R, Xtp.R, sizeof(X.R)); memcpy(X.t, Xtp.pos, sizeof(X.t));
+            memcpy(IL.R, Xtp.RLI, sizeof(IL.R)); memcpy(IL.t, Xtp.tLI, sizeof(IL.t));
+            float g[3];
+            rt_apply(rt_mul(X, IL), xyz + 3 * p, g);            /* Xtp * Xtp.I_Rt_L() * p */
+            rt_apply(back, g, xyz_out + 3 * no);
+            ++no;
+            ++p;
+        }
+    }
+    return no;
+}
+
+}  // extern "C"

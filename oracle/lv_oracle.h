@@ -120,6 +120,29 @@ void lvo_last_timing(double* knn_s, double* total_s);
 /* OpenMP team size of the match loop (MP_PROC_NUM, CMakeLists.txt:19-36); default 1 */
 void lvo_set_threads(int n);
 
+/* ---- deskew: Compensator::compensate and its State arithmetic -------------------------
+ * `State` of include/Headers/Objects.hpp:97-120, single precision like the reference.                        */
+typedef struct lvo_state32 {
+    float R[9];            /* row-major */
+    float pos[3], vel[3], bw[3], ba[3], g[3];
+    float RLI[9], tLI[3];
+    float a[3], w[3];      /* last controls */
+    double time;
+} lvo_state32;
+/* State(const state_ikfom&, double) (State.cpp:51-62); a, w = the IMU sample following `time` (State.cpp:45-48) */
+void lvo_state_from_ikfom(const double* x26, double time, const float a[3], const float w[3],
+                          const float initial_gravity[3], lvo_state32* out);
+/* State::operator+=(IMU) = update (State.cpp:122-132) -> propagate_f (State.cpp:103-120) */
+void lvo_state_add_imu(lvo_state32* s, const float a[3], const float w[3], double time);
+/* Compensator::upsample (Compensator.cpp:73-113): returns the number of states written (<= cap) */
+int lvo_upsample(const lvo_state32* states, int ns, const float* imu_a, const float* imu_w, const double* imu_t, int ni,
+                 lvo_state32* out, int cap);
+/* Compensator::get_t2 (Compensator.cpp:55-63) */
+void lvo_get_t2(const lvo_state32* states, int ns, double t2, lvo_state32* out);
+/* Compensator::compensate (Compensator.cpp:123-146): time-sorted points; returns the number of points written */
+int64_t lvo_compensate(const lvo_state32* states, int ns, const lvo_state32* Xt2, const float* xyz, const double* t,
+                       int64_t n, float* xyz_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -318,3 +318,60 @@ def last_timing():
     b = C.c_double(0)
     lib().lvo_last_timing(C.byref(a), C.byref(b))
     return a.value, b.value
+
+
+# ---- deskew (Compensator) ---------------------------------------------------------------------
+class State32(C.Structure):
+    _fields_ = [("R", C.c_float * 9), ("pos", C.c_float * 3), ("vel", C.c_float * 3), ("bw", C.c_float * 3),
+                ("ba", C.c_float * 3), ("g", C.c_float * 3), ("RLI", C.c_float * 9), ("tLI", C.c_float * 3),
+                ("a", C.c_float * 3), ("w", C.c_float * 3), ("time", C.c_double)]
+
+    def as_tuple(self):
+        return tuple(np.array(getattr(self, k)[:], dtype=np.float32).tobytes() for k, _ in self._fields_[:-1]) + (self.time,)
+
+
+def _f3(v):
+    return (C.c_float * 3)(*[float(t) for t in v])
+
+
+def state_from_ikfom(x, time, a, w, initial_gravity):
+    out = State32()
+    lib().lvo_state_from_ikfom(_d(np.ascontiguousarray(x, np.float64)), C.c_double(time), _f3(a), _f3(w),
+                               _f3(initial_gravity), C.byref(out))
+    return out
+
+
+def state_add_imu(state, a, w, time):
+    out = State32.from_buffer_copy(state)
+    lib().lvo_state_add_imu(C.byref(out), _f3(a), _f3(w), C.c_double(time))
+    return out
+
+
+def upsample(states, imu_a, imu_w, imu_t):
+    ns, ni = len(states), len(imu_t)
+    arr = (State32 * ns)(*states)
+    a = np.ascontiguousarray(imu_a, np.float32).reshape(ni, 3)
+    w = np.ascontiguousarray(imu_w, np.float32).reshape(ni, 3)
+    t = np.ascontiguousarray(imu_t, np.float64)
+    cap = ns + ni + 8
+    out = (State32 * cap)()
+    n = lib().lvo_upsample(arr, ns, _f(a), _f(w), _d(t), ni, out, cap)
+    assert n <= cap
+    return [State32.from_buffer_copy(out[i]) for i in range(n)]
+
+
+def get_t2(path, t2):
+    arr = (State32 * len(path))(*path)
+    out = State32()
+    lib().lvo_get_t2(arr, len(path), C.c_double(t2), C.byref(out))
+    return out
+
+
+def compensate(path, Xt2, xyz, t):
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    t = np.ascontiguousarray(t, np.float64)
+    out = np.zeros_like(xyz)
+    arr = (State32 * len(path))(*path)
+    lib().lvo_compensate.restype = C.c_int64
+    n = lib().lvo_compensate(arr, len(path), C.byref(Xt2), _f(xyz), _d(t), C.c_int64(xyz.shape[0]), _f(out))
+    return out[:n]
