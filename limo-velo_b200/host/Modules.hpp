@@ -130,11 +130,32 @@ class Localizator {
     Context& ctx;
 };
 
-/* The sweep handed to correct() is already deskewed and downsampled in this scope. */
+/* Deskew on the GPU (lv_compensate); the voxel-grid downsample is SURVEY 8f-3, not in this scope yet. */
 class Compensator {
    public:
-    Points compensate(const Points& sweep) { return sweep; }                   /* Compensator.cpp:18-34 */
-    Points downsample(const Points& sweep) { return sweep; }                   /* Compensator.cpp:148-163 */
+    explicit Compensator(Context& c) : ctx(c) {}
+    /* Compensator::compensate(states, Xt2, points) (Compensator.cpp:123-146): `path` as Compensator::upsample
+     * leaves it (lv_compensator_upsample), `Xt2` from lv_compensator_get_t2; points sorted by time */
+    Points compensate(const std::vector<lv_state32>& path, const lv_state32& Xt2, const Points& sweep) {
+        if (sweep.empty()) return Points();                                    /* Compensator.cpp:24 */
+        std::vector<float> xyz(3 * sweep.size()), out(3 * sweep.size());
+        std::vector<double> t(sweep.size());
+        for (size_t i = 0; i < sweep.size(); ++i) {
+            xyz[3 * i] = sweep[i].x; xyz[3 * i + 1] = sweep[i].y; xyz[3 * i + 2] = sweep[i].z;
+            t[i] = sweep[i].time;
+        }
+        if (lv_compensate(ctx.h, path.data(), (int32_t)path.size(), &Xt2, xyz.data(), t.data(), (int64_t)sweep.size(),
+                          out.data()) != LV_OK)
+            throw std::runtime_error(lv_last_error());
+        Points res = sweep;                                                    /* attributes ride along (RotTransl.cpp:43-48) */
+        for (size_t i = 0; i < res.size(); ++i) { res[i].x = out[3 * i]; res[i].y = out[3 * i + 1]; res[i].z = out[3 * i + 2]; }
+        return res;
+    }
+    Points compensate(const Points& sweep) { return sweep; }                   /* a sweep that arrives deskewed (synthetic reader) */
+    Points downsample(const Points& sweep) { return sweep; }                   /* Compensator.cpp:148-163: 8f-3 */
+
+   private:
+    Context& ctx;
 };
 
 /* Plain time-ordered buffers (Accumulator.hpp:61-74), fed by a reader instead of ROS callbacks. */

@@ -27,7 +27,7 @@ int main(int argc, char** argv) {
         lv::Context ctx(prm);
         lv::Mapper map(ctx);
         lv::Localizator loc(ctx);
-        lv::Compensator comp;
+        lv::Compensator comp(ctx);
         lv::Accumulator accum;
 
         lv_synth_world* world = lv_synth_world_create(20260924, map_points);
