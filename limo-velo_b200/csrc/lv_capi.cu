@@ -487,8 +487,7 @@ static lv_status enqueue_update(lv_context* h, const float* d_xyz, int64_t n) {
     int n32 = (int)n;
     uint32_t* counters = h->d_hard_list + h->prm.max_points;
     void* args[5] = {&c, &job, &d_xyz, &n32, &counters};
-    cudaKernelNodeParams kp;
-    memset(&kp, 0, sizeof(kp));
+    cudaKernelNodeParams kp = {};
     kp.func = const_cast<void*>(ieskf_begin_kernel_ptr());
     kp.gridDim = dim3(1, 1, 1);
     kp.blockDim = dim3(256, 1, 1);
@@ -500,8 +499,7 @@ static lv_status enqueue_update(lv_context* h, const float* d_xyz, int64_t n) {
         measure_kernel_shapes(a, measure_grid((int)cap), shape);
         void* margs[1] = {&a};
         for (int k = 0; k < kMeasureKernels; ++k) {
-            cudaKernelNodeParams mp;
-            memset(&mp, 0, sizeof(mp));
+            cudaKernelNodeParams mp = {};
             mp.func = const_cast<void*>(shape[k].func);
             mp.gridDim = dim3(shape[k].grid, 1, 1);
             mp.blockDim = dim3(shape[k].block, 1, 1);

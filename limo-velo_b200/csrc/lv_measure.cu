@@ -527,8 +527,7 @@ void measure_kernel_shapes(const MeasureArgs& a, int grid, MeasureKernelShape ou
 /* <<<>>> with the programmatic-dependent-launch attribute when `pdl` (see pdl_wait above) */
 template <class... Params, class... Args>
 static cudaError_t launch_k(void (*kernel)(Params...), unsigned grid, unsigned block, cudaStream_t st, bool pdl, Args... args) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid, 1, 1);
     cfg.blockDim = dim3(block, 1, 1);
     cfg.stream = st;
