@@ -334,6 +334,31 @@ def run_native(args, rank, local_rank, world_size):
     except Exception as e:                                         # never let the side measurement break the headline
         deskew = {"error": str(e)}
 
+    # ---- downsamplers, reported beside the headline ----
+    downsample = None
+    try:
+        d_in, d_out = loc.upload(sweeps[0]), loc.device_alloc(n * 12)
+        for _ in range(3):
+            m = loc.voxelgrid_downsample_device(d_in, n, 0.5, d_out)
+        reps = 30
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            m = loc.voxelgrid_downsample_device(d_in, n, 0.5, d_out)             # blocking: 10 launches + count read-back
+        dt_vg = (time.perf_counter() - t0) / reps
+        loc.device_free(d_in); loc.device_free(d_out)
+        raw = np.ascontiguousarray(np.tile(sweeps[0], (4, 1)))                    # a raw message at downsample_rate 4
+        loc.temporal_downsample(raw, 4, 4.0)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            kept, _ = loc.temporal_downsample(raw, 4, 4.0)
+        dt_td = (time.perf_counter() - t0) / 10
+        downsample = {"voxelgrid_points": n, "voxelgrid_leaves": int(m), "leaf_m": 0.5,
+                      "lv_voxelgrid_downsample_device_ms": 1e3 * dt_vg,
+                      "temporal_points": int(raw.shape[0]), "temporal_kept": int(kept.shape[0]),
+                      "lv_temporal_downsample_host_ms": 1e3 * dt_td, "note": "blocking calls, wall clock"}
+    except Exception as e:
+        downsample = {"error": str(e)}
+
     # ---- max over ranks / totals ----
     tot = torch.tensor([step_ms, float(pts), float(matched), e2e_s, float(e2e_pts), float(launches)],
                        dtype=torch.float64, device="cuda")
@@ -400,7 +425,7 @@ def run_native(args, rank, local_rank, world_size):
                          "kernel": dominant, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_POINT * n},
             "cpu_baseline": cpu,
             "map_update": {"lv_map_add_ms": 1e3 * min(t_add), "points_added": n, "map_points": loc.map_size()},
-            "deskew": deskew,
+            "deskew": deskew, "downsample": downsample,
             "final_position_error_m": pose_err,
             "clocks": clock_info,
         }

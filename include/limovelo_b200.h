@@ -218,6 +218,22 @@ lv_status lv_compensate(lv_handle h, const lv_state32* path, int32_t ns, const l
 lv_status lv_compensate_device(lv_handle h, const lv_state32* path, int32_t ns, const lv_state32* Xt2,
                                const float* d_xyz, const double* d_t, int64_t n, float* d_xyz_out);
 
+/* ---- downsamplers in front of the path -------------------------------------------- */
+/* PointCloudProcessor::downsample -> temporal_downsample (src/Utils/PointCloudProcessor.cpp:18-21,101-112): keeps
+ * point i iff (downsample_rate <= 1 or (i + 1) % downsample_rate == 0) and min_dist < |p|, order preserved.
+ * HOST buffers; xyz_out (n x 3) and idx_out (n, may be NULL: indices of the kept points, for the caller's other
+ * per-point fields) receive *n_out entries.                                                             */
+lv_status lv_temporal_downsample(lv_handle h, const float* xyz, int64_t n, int32_t downsample_rate, double min_dist,
+                                 float* xyz_out, int32_t* idx_out, int64_t* n_out);
+/* Compensator::downsample -> voxelgrid_downsample (src/Modules/Compensator.cpp:115-118,148-163): pcl::VoxelGrid with
+ * leaf downsample_prec: one centroid per occupied leaf, leaves in ascending PCL cell index.  xyz_out needs room for
+ * n points.  LV_ERR_ARG when the leaf is too small for the extent (PCL refuses and returns the input).      */
+lv_status lv_voxelgrid_downsample(lv_handle h, const float* xyz, int64_t n, float downsample_prec, float* xyz_out,
+                                  int64_t* n_out);
+/* the same on device-resident buffers (d_xyz_out must not alias d_xyz)                                    */
+lv_status lv_voxelgrid_downsample_device(lv_handle h, const float* d_xyz, int64_t n, float downsample_prec,
+                                         float* d_xyz_out, int64_t* n_out);
+
 /* ---- synthetic reader (replaces the ROS subscribers of src/main.cpp:27-39) ---- */
 typedef struct lv_synth_world lv_synth_world;
 /* seeded "city-block" world whose surface sampling holds exactly m map points              */

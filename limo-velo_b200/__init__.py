@@ -370,6 +370,27 @@ class Localizer:
         return _check(self.L.lv_compensate_device(self.h, arr, len(path), C.byref(Xt2), C.c_void_p(d_xyz), C.c_void_p(d_t),
                                                   C.c_int64(n), C.c_void_p(d_out)))
 
+    def temporal_downsample(self, xyz, rate, min_dist):
+        """PointCloudProcessor::temporal_downsample: returns (kept points, their indices)"""
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        out, idx, n = np.empty_like(xyz), np.empty(xyz.shape[0], np.int32), C.c_int64(0)
+        _check(self.L.lv_temporal_downsample(self.h, _f(xyz), C.c_int64(xyz.shape[0]), C.c_int32(rate), C.c_double(min_dist),
+                                             _f(out), idx.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(n)))
+        return out[:n.value].copy(), idx[:n.value].copy()
+
+    def voxelgrid_downsample(self, xyz, leaf):
+        """Compensator::voxelgrid_downsample (pcl::VoxelGrid centroids)"""
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        out, n = np.empty_like(xyz), C.c_int64(0)
+        _check(self.L.lv_voxelgrid_downsample(self.h, _f(xyz), C.c_int64(xyz.shape[0]), C.c_float(leaf), _f(out), C.byref(n)))
+        return out[:n.value].copy()
+
+    def voxelgrid_downsample_device(self, d_xyz, n, leaf, d_out):
+        m = C.c_int64(0)
+        _check(self.L.lv_voxelgrid_downsample_device(self.h, C.c_void_p(d_xyz), C.c_int64(n), C.c_float(leaf), C.c_void_p(d_out),
+                                                     C.byref(m)))
+        return m.value
+
     def correct_buffers(self):
         """preallocated outputs for correct_raw (benchmarks: keeps numpy / ctypes construction out of the timed call)"""
         return dict(logs=(IterLog * MAX_EVALS)(), ne=C.c_int32(0), x=np.zeros(STATE_LEN), P=np.zeros((DOF, DOF)))

@@ -66,6 +66,10 @@ struct lv_context {
     float* d_deskew_in = nullptr;      /* max_points x 3 */
     int* d_bad = nullptr;
     int* h_bad = nullptr;              /* pinned */
+    DownsampleScratch ds;              /* downsamplers: grows with the largest cloud seen */
+    float* d_ds_in = nullptr;          /* staging for the host-buffer variants */
+    float* d_ds_out = nullptr;
+    int64_t ds_stage_cap = 0;
     double* d_reduced = nullptr;       /* 157 doubles */
     double* h_reduced = nullptr;       /* pinned */
     void* d_flush = nullptr;
@@ -270,6 +274,7 @@ void lv_destroy(lv_handle h) {
     for (auto& u : h->graphs) { cudaGraphExecDestroy(u.exec); cudaGraphDestroy(u.graph); }
     cudaFree(h->d_job); cudaFree(h->d_ref); cudaFree(h->d_redo);
     cudaFree(h->d_path); cudaFreeHost(h->h_path); cudaFree(h->d_times); cudaFree(h->d_deskew_in); cudaFree(h->d_bad); cudaFreeHost(h->h_bad);
+    ds_free(h->ds); cudaFree(h->d_ds_in); cudaFree(h->d_ds_out);
     MapBuffers& m = h->map;
     cudaFree(m.xyz); cudaFree(m.xyz_alt); cudaFree(m.keys); cudaFree(m.keys_sorted); cudaFree(m.vals); cudaFree(m.vals_sorted);
     cudaFree(m.pts);
@@ -748,6 +753,68 @@ lv_status lv_compensate(lv_handle h, const lv_state32* path, int32_t ns, const l
     LV_CUDA(cudaMemcpyAsync(xyz_out, h->d_deskew_in, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, h->stream));
     LV_CUDA(cudaStreamSynchronize(h->stream));
     if (*h->h_bad) { set_error("deskew: a timestamp lies outside the path or the points are not time-sorted"); return LV_ERR_ARG; }
+    return LV_OK;
+}
+
+/* ---- downsamplers ------------------------------------------------------------------------------- */
+static lv_status ds_stage(lv_context* h, int64_t n) {
+    if (n <= h->ds_stage_cap) return LV_OK;
+    cudaFree(h->d_ds_in); cudaFree(h->d_ds_out);
+    h->d_ds_in = h->d_ds_out = nullptr;
+    h->ds_stage_cap = 0;
+    const int64_t cap = n + n / 4 + 1024;
+    LV_CUDA(cudaMalloc(&h->d_ds_in, sizeof(float) * 3 * cap));
+    LV_CUDA(cudaMalloc(&h->d_ds_out, sizeof(float) * 3 * cap));
+    h->ds_stage_cap = cap;
+    return LV_OK;
+}
+lv_status lv_voxelgrid_downsample_device(lv_handle h, const float* d_xyz, int64_t n, float leaf, float* d_xyz_out, int64_t* n_out) {
+    if (!h || !d_xyz || !d_xyz_out || !n_out || n < 0 || !(leaf > 0.f) || n > 0x7fffffff) return LV_ERR_ARG;
+    *n_out = 0;
+    if (n == 0) return LV_OK;
+    LV_CUDA(cudaSetDevice(h->prm.device));
+    LV_CUDA(ds_reserve(h->ds, n));
+    int launches = 0;
+    LV_CUDA(launch_voxelgrid(h->ds, d_xyz, n, leaf, d_xyz_out, h->stream, &launches));
+    h->prof.total_launches += launches;
+    LV_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->ds.h_count[1]) { set_error("voxel grid: leaf size too small for the extent of the cloud (cell index overflows)"); return LV_ERR_ARG; }
+    *n_out = h->ds.h_count[0];
+    return LV_OK;
+}
+lv_status lv_voxelgrid_downsample(lv_handle h, const float* xyz, int64_t n, float leaf, float* xyz_out, int64_t* n_out) {
+    if (!h || !xyz || !xyz_out || !n_out || n < 0 || !(leaf > 0.f) || n > 0x7fffffff) return LV_ERR_ARG;
+    *n_out = 0;
+    if (n == 0) return LV_OK;
+    LV_CUDA(cudaSetDevice(h->prm.device));
+    lv_status s = ds_stage(h, n);
+    if (s != LV_OK) return s;
+    LV_CUDA(cudaMemcpyAsync(h->d_ds_in, xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
+    s = lv_voxelgrid_downsample_device(h, h->d_ds_in, n, leaf, h->d_ds_out, n_out);
+    if (s != LV_OK) return s;
+    LV_CUDA(cudaMemcpyAsync(xyz_out, h->d_ds_out, sizeof(float) * 3 * (size_t)*n_out, cudaMemcpyDeviceToHost, h->stream));
+    LV_CUDA(cudaStreamSynchronize(h->stream));
+    return LV_OK;
+}
+lv_status lv_temporal_downsample(lv_handle h, const float* xyz, int64_t n, int32_t rate, double min_dist, float* xyz_out,
+                                 int32_t* idx_out, int64_t* n_out) {
+    if (!h || !xyz || !xyz_out || !n_out || n < 0 || n > 0x7fffffff) return LV_ERR_ARG;
+    *n_out = 0;
+    if (n == 0) return LV_OK;
+    LV_CUDA(cudaSetDevice(h->prm.device));
+    lv_status s = ds_stage(h, n);
+    if (s != LV_OK) return s;
+    LV_CUDA(ds_reserve(h->ds, n));
+    LV_CUDA(cudaMemcpyAsync(h->d_ds_in, xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
+    int launches = 0;
+    LV_CUDA(launch_temporal(h->ds, h->d_ds_in, n, rate, min_dist, h->d_ds_out, nullptr, h->stream, &launches));
+    h->prof.total_launches += launches;
+    LV_CUDA(cudaStreamSynchronize(h->stream));
+    const int64_t m = h->ds.h_count[0];
+    LV_CUDA(cudaMemcpyAsync(xyz_out, h->d_ds_out, sizeof(float) * 3 * (size_t)m, cudaMemcpyDeviceToHost, h->stream));
+    if (idx_out) LV_CUDA(cudaMemcpyAsync(idx_out, h->ds.sel, sizeof(int32_t) * (size_t)m, cudaMemcpyDeviceToHost, h->stream));
+    LV_CUDA(cudaStreamSynchronize(h->stream));
+    *n_out = m;
     return LV_OK;
 }
 

@@ -114,6 +114,25 @@ cudaError_t launch_reduce_partials(const double* partials, int n_partials, doubl
 cudaError_t launch_set_frame(UpdateCtrl* c, cudaStream_t st);   /* frame from c->x, done = 0 */
 cudaError_t launch_l2_flush(void* buf, size_t bytes, cudaStream_t st);
 
+/* lv_downsample.cu: PointCloudProcessor::temporal_downsample and Compensator::voxelgrid_downsample */
+struct DownsampleScratch {
+    int64_t cap = 0;
+    uint32_t *keys = nullptr, *keys_sorted = nullptr, *vals = nullptr, *vals_sorted = nullptr;
+    uint8_t* flags = nullptr;
+    int32_t* sel = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    void* box = nullptr;           /* GridBox */
+    int* count = nullptr;
+    int* h_count = nullptr;        /* pinned: [0] output count, [1] overflow flag */
+};
+cudaError_t ds_reserve(DownsampleScratch& s, int64_t n);
+void ds_free(DownsampleScratch& s);
+cudaError_t launch_voxelgrid(DownsampleScratch& s, const float* d_xyz, int64_t n, float leaf, float* d_out, cudaStream_t st,
+                             int* launches);
+cudaError_t launch_temporal(DownsampleScratch& s, const float* d_xyz, int64_t n, int rate, double min_dist, float* d_out,
+                            int32_t* d_idx_out, cudaStream_t st, int* launches);
+
 /* lv_deskew.cu: Compensator::compensate.  d_bad (one int) is set when a timestamp is out of range / out of order */
 int deskew_max_states();
 cudaError_t launch_deskew(const lv_state32* d_path, int ns, const lv_state32& Xt2, double t_lo, double t_hi,

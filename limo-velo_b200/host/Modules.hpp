@@ -130,7 +130,7 @@ class Localizator {
     Context& ctx;
 };
 
-/* Deskew on the GPU (lv_compensate); the voxel-grid downsample is SURVEY 8f-3, not in this scope yet. */
+/* Deskew (lv_compensate) and voxel-grid downsample (lv_voxelgrid_downsample) on the GPU. */
 class Compensator {
    public:
     explicit Compensator(Context& c) : ctx(c) {}
@@ -152,7 +152,19 @@ class Compensator {
         return res;
     }
     Points compensate(const Points& sweep) { return sweep; }                   /* a sweep that arrives deskewed (synthetic reader) */
-    Points downsample(const Points& sweep) { return sweep; }                   /* Compensator.cpp:148-163: 8f-3 */
+    /* Compensator::downsample -> voxelgrid_downsample (Compensator.cpp:115-118,148-163): centroids carry xyz only */
+    Points downsample(const Points& sweep, float downsample_prec) {
+        if (sweep.empty()) return Points();
+        std::vector<float> xyz(3 * sweep.size()), out(3 * sweep.size());
+        for (size_t i = 0; i < sweep.size(); ++i) { xyz[3 * i] = sweep[i].x; xyz[3 * i + 1] = sweep[i].y; xyz[3 * i + 2] = sweep[i].z; }
+        int64_t m = 0;
+        if (lv_voxelgrid_downsample(ctx.h, xyz.data(), (int64_t)sweep.size(), downsample_prec, out.data(), &m) != LV_OK)
+            return sweep;                                                      /* PCL returns the input when it refuses */
+        Points res((size_t)m);
+        for (int64_t i = 0; i < m; ++i) res[(size_t)i] = Point{out[3 * i], out[3 * i + 1], out[3 * i + 2], 0.0};
+        return res;
+    }
+    Points downsample(const Points& sweep) { return sweep; }                   /* a sweep that arrives downsampled */
 
    private:
     Context& ctx;

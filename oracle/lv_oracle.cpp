@@ -1589,3 +1589,67 @@ int64_t lvo_compensate(const lvo_state32* states, int ns, const lvo_state32* Xt2
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// Downsampling.  PARITY UNPINNED for the voxel grid: PCL is not in this image; the
+// restatement follows pcl/filters/impl/voxel_grid.hpp (1.8-1.12: applyFilter, downsample_all_data_ = true ->
+// CentroidPoint -> AccumulatorXYZ) as called from Compensator.cpp:148-163.
+// ------------------------------------------------------------------------------------------
+#include <algorithm>
+#include <limits>
+
+extern "C" {
+
+int64_t lvo_temporal_downsample(const float* xyz, int64_t n, int rate, double min_dist, int32_t* idx_out) {
+    int64_t no = 0;
+    int ds_counter = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const bool keep = rate <= 1 || (++ds_counter % rate == 0);              /* PointCloudProcessor.cpp:107 */
+        const float* p = xyz + 3 * i;
+        const float nrm = sqrtf((p[0] * p[0] + p[1] * p[1]) + p[2] * p[2]);     /* Eigen Vector3f::norm() */
+        if (keep && min_dist < (double)nrm) idx_out[no++] = (int32_t)i;         /* :108 */
+    }
+    return no;
+}
+
+int64_t lvo_voxelgrid_downsample(const float* xyz, int64_t n, float leaf, float* xyz_out, int64_t cap) {
+    if (n <= 0) return 0;
+    const float inv = 1.0f / leaf;                                             /* inverse_leaf_size_ = 1 / leaf_size_ */
+    float mn[3] = {std::numeric_limits<float>::max(), std::numeric_limits<float>::max(), std::numeric_limits<float>::max()};
+    float mx[3] = {-mn[0], -mn[0], -mn[0]};
+    for (int64_t i = 0; i < n; ++i)                                            /* getMinMax3D */
+        for (int a = 0; a < 3; ++a) { mn[a] = std::min(mn[a], xyz[3 * i + a]); mx[a] = std::max(mx[a], xyz[3 * i + a]); }
+    int64_t d[3];
+    for (int a = 0; a < 3; ++a) d[a] = (int64_t)((mx[a] - mn[a]) * inv) + 1;
+    if (d[0] * d[1] * d[2] > (int64_t)std::numeric_limits<int32_t>::max()) return -1;
+    int minb[3], divb[3];
+    for (int a = 0; a < 3; ++a) {
+        minb[a] = (int)floorf(mn[a] * inv);
+        divb[a] = (int)floorf(mx[a] * inv) - minb[a] + 1;
+    }
+    const int mul[3] = {1, divb[0], divb[0] * divb[1]};
+    std::vector<std::pair<unsigned, int64_t>> iv((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        int idx = 0;
+        for (int a = 0; a < 3; ++a) idx += (int)(floorf(xyz[3 * i + a] * inv) - (float)minb[a]) * mul[a];
+        iv[(size_t)i] = std::make_pair((unsigned)idx, i);
+    }
+    std::stable_sort(iv.begin(), iv.end(), [](const std::pair<unsigned, int64_t>& a, const std::pair<unsigned, int64_t>& b) { return a.first < b.first; });
+    int64_t no = 0;
+    for (size_t i = 0; i < iv.size();) {
+        size_t j = i;
+        float s[3] = {0.f, 0.f, 0.f};
+        while (j < iv.size() && iv[j].first == iv[i].first) {                 /* AccumulatorXYZ: xyz += p */
+            for (int a = 0; a < 3; ++a) s[a] += xyz[3 * iv[j].second + a];
+            ++j;
+        }
+        const float cnt = (float)(j - i);
+        if (no < cap)
+            for (int a = 0; a < 3; ++a) xyz_out[3 * no + a] = s[a] / cnt;     /* xyz / n */
+        ++no;
+        i = j;
+    }
+    return no;
+}
+
+}  // extern "C"

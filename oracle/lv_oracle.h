@@ -143,6 +143,16 @@ void lvo_get_t2(const lvo_state32* states, int ns, double t2, lvo_state32* out);
 int64_t lvo_compensate(const lvo_state32* states, int ns, const lvo_state32* Xt2, const float* xyz, const double* t,
                        int64_t n, float* xyz_out);
 
+/* ---- downsampling ------------------------------------------------------------------------
+ * PointCloudProcessor::temporal_downsample (src/Utils/PointCloudProcessor.cpp:101-112): keeps point i iff
+ * (rate <= 1 or (i + 1) % rate == 0) and min_dist < |p|; returns the number kept, their indices in idx_out.    */
+int64_t lvo_temporal_downsample(const float* xyz, int64_t n, int rate, double min_dist, int32_t* idx_out);
+/* Compensator::voxelgrid_downsample (Compensator.cpp:148-163) = pcl::VoxelGrid with leaf `leaf`: one centroid per
+ * occupied leaf, leaves in ascending PCL cell index, fp32 sums.  PCL sorts (cell, point) pairs with an unstable
+ * sort, so the summation order inside a leaf is unspecified upstream; this restatement uses input order.
+ * Returns the number of leaves (writes at most cap centroids); -1 if PCL would refuse (cell index overflow).   */
+int64_t lvo_voxelgrid_downsample(const float* xyz, int64_t n, float leaf, float* xyz_out, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -375,3 +375,23 @@ def compensate(path, Xt2, xyz, t):
     lib().lvo_compensate.restype = C.c_int64
     n = lib().lvo_compensate(arr, len(path), C.byref(Xt2), _f(xyz), _d(t), C.c_int64(xyz.shape[0]), _f(out))
     return out[:n]
+
+
+# ---- downsampling ---------------------------------------------------------------------------------
+def temporal_downsample(xyz, rate, min_dist):
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    idx = np.zeros(xyz.shape[0], np.int32)
+    lib().lvo_temporal_downsample.restype = C.c_int64
+    n = lib().lvo_temporal_downsample(_f(xyz), C.c_int64(xyz.shape[0]), C.c_int(rate), C.c_double(min_dist),
+                                      idx.ctypes.data_as(C.POINTER(C.c_int32)))
+    return idx[:n]
+
+
+def voxelgrid_downsample(xyz, leaf):
+    xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    out = np.zeros_like(xyz)
+    lib().lvo_voxelgrid_downsample.restype = C.c_int64
+    n = lib().lvo_voxelgrid_downsample(_f(xyz), C.c_int64(xyz.shape[0]), C.c_float(leaf), _f(out), C.c_int64(xyz.shape[0]))
+    if n < 0:
+        raise ValueError("leaf size too small for the extent of the cloud (PCL refuses)")
+    return out[:n]
