@@ -54,7 +54,7 @@ struct lv_context {
     double* d_partials = nullptr;
     int4* d_nn_a = nullptr;            /* max_points: K1 -> K2 hand-over */
     int2* d_nn_b = nullptr;
-    uint32_t* d_hard_list = nullptr;   /* max_points + 3: work list of K1b, its length, a spare word, redo length */
+    uint32_t* d_hard_list = nullptr;   /* kHardBuckets segments of hard_segment(max_points) entries, then kCounters counters */
     float4* d_ref = nullptr;           /* max_points: reuse reference (lv_reuse_kernel) */
     uint32_t* d_redo = nullptr;        /* max_points */
     bool use_reuse = true;
@@ -179,7 +179,8 @@ static MeasureArgs make_measure_args(lv_context* h, const float* d_xyz, int64_t 
     a.nn_a = h->d_nn_a;
     a.nn_b = h->d_nn_b;
     a.hard_list = h->d_hard_list;
-    a.hard_count = h->d_hard_list + h->prm.max_points;
+    a.hard_seg = hard_segment(h->prm.max_points);
+    a.hard_count = h->d_hard_list + (size_t)kHardBuckets * a.hard_seg;
     return a;
 }
 
@@ -241,7 +242,7 @@ lv_status lv_create(const lv_params* p, lv_handle* out) {
     LV_CUDA(cudaMalloc(&h->d_sweep, sizeof(float) * 3 * p->max_points));
     LV_CUDA(cudaMalloc(&h->d_nn_a, sizeof(int4) * p->max_points));
     LV_CUDA(cudaMalloc(&h->d_nn_b, sizeof(int2) * p->max_points));
-    LV_CUDA(cudaMalloc(&h->d_hard_list, sizeof(uint32_t) * (p->max_points + 3)));
+    LV_CUDA(cudaMalloc(&h->d_hard_list, sizeof(uint32_t) * ((size_t)kHardBuckets * hard_segment(p->max_points) + kCounters)));
     LV_CUDA(cudaMalloc(&h->d_ref, sizeof(float4) * p->max_points));
     LV_CUDA(cudaMalloc(&h->d_redo, sizeof(uint32_t) * (p->max_points + 64)));   /* + one block of slack: read speculatively */
     h->use_reuse = getenv("LV_NO_REUSE") == nullptr;
@@ -490,7 +491,7 @@ static lv_status enqueue_update(lv_context* h, const float* d_xyz, int64_t n) {
     UpdateCtrl* c = h->d_ctrl;
     MeasureJob* job = h->d_job;
     int n32 = (int)n;
-    uint32_t* counters = h->d_hard_list + h->prm.max_points;
+    uint32_t* counters = h->d_hard_list + (size_t)kHardBuckets * hard_segment(h->prm.max_points);
     void* args[5] = {&c, &job, &d_xyz, &n32, &counters};
     cudaKernelNodeParams kp = {};
     kp.func = const_cast<void*>(ieskf_begin_kernel_ptr());
@@ -520,7 +521,7 @@ static lv_status enqueue_update(lv_context* h, const float* d_xyz, int64_t n) {
 
 static lv_status enqueue_update_kernels(lv_context* h, const float* d_xyz, int64_t n, bool as_job) {
     const int pdl = (h->use_pdl && !h->profile) ? 1 : 0;
-    uint32_t* counters = h->d_hard_list + h->prm.max_points;
+    uint32_t* counters = h->d_hard_list + (size_t)kHardBuckets * hard_segment(h->prm.max_points);
     LV_CUDA(launch_ieskf_begin(h->d_ctrl, as_job ? h->d_job : nullptr, d_xyz, (int)n, counters, h->stream));
     if (!as_job) h->prof.total_launches += 1;
     MeasureArgs a = update_measure_args(h, d_xyz, n, as_job);

@@ -14,6 +14,11 @@
 namespace lv {
 
 enum { kMeasureThreads = 128, kPartialStride = 96, kStepThreads = 512 };
+/* The search kernel appends its uncertified queries to one of 32 lists picked by block index: thousands of atomics on
+ * ONE counter cost it a 9 us tail on the first evaluation of an update (tools/timeline.py). */
+enum { kHardBuckets = 32, kCounters = 4 + kHardBuckets };
+/* a bucket receives the queries of every 32nd block: at most n / 32 + (queries per block <= 128) of them */
+inline uint32_t hard_segment(int64_t n) { return (uint32_t)((n + kHardBuckets - 1) / kHardBuckets + 160); }
 
 /* the sweep of an update replayed from a CUDA graph: written by the begin kernel (whose arguments are the
  * only thing patched per launch), read by the measurement kernels instead of MeasureArgs::xyz / n / n_tiles */
@@ -48,8 +53,9 @@ struct MeasureArgs {
     double* rows;              /* n x 13 (row[12], h)                                     */
     int4* nn_a;                /* n: search result handed from K1 to K2 (neighbours 0..3)      */
     int2* nn_b;                /* n: (neighbour 4, bits of the 5th squared distance)         */
-    uint32_t* hard_list;       /* n: queries level 0 could not certify (K1 -> K1b)           */
-    uint32_t* hard_count;      /* [0] length of hard_list, [1] spare, [2] length of redo_list */
+    uint32_t* hard_list;       /* queries level 0 could not certify (K1 -> K1b): kHardBuckets segments of hard_seg entries */
+    uint32_t hard_seg;         /* capacity of one segment                                      */
+    uint32_t* hard_count;      /* [2] length of redo_list, [4 .. 4 + kHardBuckets) lengths of the segments; kCounters words */
     /* reuse of neighbours across the evaluations of one update (NULL: off) */
     float4* ref;               /* n: world position the stored neighbours were searched from + outsider bound */
     uint32_t* redo_list;       /* n: queries whose neighbours could not be reused (Kv -> K1)  */

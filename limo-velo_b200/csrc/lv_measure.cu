@@ -21,6 +21,12 @@
 #include <stdlib.h>
 #include <string.h>
 
+#ifdef LV_STEP_TIMING
+__device__ unsigned long long g_probes[2];     /* total hash probes, number of lookups that needed more than 8 */
+#ifdef __CUDA_ARCH__
+#define LV_PROBE_COUNT() do { atomicAdd(&g_probes[0], 1ull); } while (0)
+#endif
+#endif
 #ifdef LV_STEP_TIMING   /* tuning build only: per-phase clocks of the step kernel */
 __device__ long long g_step_clk[64];
 #ifdef __CUDA_ARCH__
@@ -31,16 +37,31 @@ __device__ long long g_step_clk[64];
 
 #include "lv_internal.h"
 
+#ifdef LV_STEP_TIMING   /* tuning build only: wall-clock timeline of the kernels of an update (graph + PDL included) */
+__device__ unsigned long long g_tl[5][8][8];   /* [scheduled | past the wait | end (thread 0) | last block past the wait | end (any warp)][evaluation][kind], ns */
+__device__ __forceinline__ unsigned long long lv_gt() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define LV_TL_SCHED() const unsigned long long tl_s_ = lv_gt()
+#define LV_TL_WORK(c, kind) const int tl_e_ = (c)->n_evals & 7; if (threadIdx.x == 0) { atomicMin(&g_tl[0][tl_e_][kind], tl_s_); const unsigned long long tw_ = lv_gt(); atomicMin(&g_tl[1][tl_e_][kind], tw_); atomicMax(&g_tl[3][tl_e_][kind], tw_); }
+#define LV_TL_END(kind) do { if (threadIdx.x == 0) atomicMax(&g_tl[2][tl_e_][kind], lv_gt()); if ((threadIdx.x & 31) == 0) atomicMax(&g_tl[4][tl_e_][kind], lv_gt()); } while (0)
+#else
+#define LV_TL_SCHED()
+#define LV_TL_WORK(c, kind)
+#define LV_TL_END(kind)
+#endif
+
 namespace lv {
 
 /* the 90 (a, b) products each block accumulates: 78 upper-triangle entries of HTH, then 12 of HTh
  * (b = 12 selects h) */
 __constant__ uint8_t c_pair_a[90];
 __constant__ uint8_t c_pair_b[90];
-static bool g_pairs_ready = false;
+static bool g_pairs_ready[64] = {false};    /* constant memory is per device */
 
 static void init_pairs() {
-    if (g_pairs_ready) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (g_pairs_ready[dev]) return;
     uint8_t a[90], b[90];
     int e = 0;
     for (int i = 0; i < 12; ++i)
@@ -48,7 +69,7 @@ static void init_pairs() {
     for (int i = 0; i < 12; ++i) { a[e] = (uint8_t)i; b[e] = 12; ++e; }
     cudaMemcpyToSymbol(c_pair_a, a, sizeof(a));
     cudaMemcpyToSymbol(c_pair_b, b, sizeof(b));
-    g_pairs_ready = true;
+    g_pairs_ready[dev] = true;
 }
 
 /* Programmatic dependent launch: every kernel of an update lets its successor's blocks be scheduled early
@@ -104,8 +125,10 @@ __device__ __forceinline__ void store_ref(const MeasureArgs& a, int qi, const fl
 template <int G, bool LIST>
 __global__ void __launch_bounds__(LV_SEARCH_THREADS) lv_search_kernel(const MeasureArgs a) {
     typedef GroupLanes<G> Grp;
+    LV_TL_SCHED();
     pdl_wait();                 /* the predecessor (begin / step / reuse kernel) writes the frame and the lists */
     pdl_trigger();
+    LV_TL_WORK(a.ctrl, 2);
     /* the search is a chain of dependent round trips (flags -> point -> slot -> bucket): everything that does
      * not depend on an earlier answer is requested up front, the `done` test included */
     const int done = a.ctrl->done;                      /* update already finished (uniform over the grid) */
@@ -137,8 +160,12 @@ __global__ void __launch_bounds__(LV_SEARCH_THREADS) lv_search_kernel(const Meas
         store_neighbours(a, qi, t, false);
         const bool hard = st == 2 || (st == 1 && !settled);
         store_ref(a, qi, g, (st == 1 && settled) ? outsider_bound(t.d5, region) : 0.f);
-        if (hard) a.hard_list[atomicAdd(a.hard_count, 1u)] = (uint32_t)qi;
+        if (hard) {
+            const uint32_t b = blockIdx.x % kHardBuckets;
+            a.hard_list[(size_t)b * a.hard_seg + atomicAdd(a.hard_count + 4 + b, 1u)] = (uint32_t)qi;
+        }
     }
+    LV_TL_END(2);
 }
 
 /*
@@ -151,6 +178,7 @@ __global__ void __launch_bounds__(128) lv_reuse_kernel(const MeasureArgs a) {
     /* Before the wait: everything but the new frame.  The sweep, the stored neighbours (written by the previous
      * evaluation's search kernels, three or more kernels ago) and the map are fetched while the step kernel
      * still runs; after the wait only the frame is missing. */
+    LV_TL_SCHED();
     const JobView jb = job_view(a);
     const int qi = (int)(blockIdx.x * blockDim.x + threadIdx.x);
     const bool have = qi < jb.n;
@@ -179,6 +207,7 @@ __global__ void __launch_bounds__(128) lv_reuse_kernel(const MeasureArgs a) {
     }
     pdl_wait();                 /* the step kernel before us writes the frame and the done flag */
     pdl_trigger();
+    LV_TL_WORK(a.ctrl, 1);
     if (a.ctrl->done) return;
     bool redo = false;
     if (have) {
@@ -201,6 +230,7 @@ __global__ void __launch_bounds__(128) lv_reuse_kernel(const MeasureArgs a) {
         base = __shfl_sync(0xffffffffu, base, leader);
         if (redo) a.redo_list[base + (uint32_t)__popc(m & ((1u << lane) - 1u))] = (uint32_t)qi;
     }
+    LV_TL_END(1);
 }
 
 /*
@@ -210,16 +240,34 @@ __global__ void __launch_bounds__(128) lv_reuse_kernel(const MeasureArgs a) {
 __global__ void __launch_bounds__(128) lv_search_upper_kernel(const MeasureArgs a) {
     /* flags, frame and job were written two or more kernels ago: safe to fetch while the search still runs
      * (a kernel triggers its successor only after its own wait, so "two kernels ago" is complete by now) */
+    LV_TL_SCHED();
     const int done = a.ctrl->done;
     const JobView jb = job_view(a);
     const Rt32 T = a.ctrl->frame.lidar_to_world;
     pdl_wait();                 /* the search kernel's work list and uncertified answers */
     pdl_trigger();
+    LV_TL_WORK(a.ctrl, 3);
     if (done) return;
-    const uint32_t n_hard = *a.hard_count;
+    /* the 32 segment lengths, one per lane, and their prefix sums */
+    const int lane = threadIdx.x & 31;
+    const uint32_t cnt = a.hard_count[4 + lane];
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    const uint32_t n_hard = __shfl_sync(0xffffffffu, incl, 31);
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t h = warp; h < n_hard; h += n_warps) {
-        const int qi = (int)a.hard_list[h];
+        int lo = 0;                                     /* first segment whose inclusive prefix exceeds h */
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+            const uint32_t v = __shfl_sync(0xffffffffu, incl, lo + step - 1);
+            if (v <= h) lo += step;
+        }
+        const uint32_t before = __shfl_sync(0xffffffffu, incl - cnt, lo);
+        const int qi = (int)a.hard_list[(size_t)lo * a.hard_seg + (h - before)];
         float g[3];
         rt_apply(T, jb.xyz[3 * qi], jb.xyz[3 * qi + 1], jb.xyz[3 * qi + 2], g);
         const int2 prev = a.nn_b[qi];   /* level 0's (uncertified) 5th distance bounds the answer from above */
@@ -231,6 +279,7 @@ __global__ void __launch_bounds__(128) lv_search_upper_kernel(const MeasureArgs 
             store_ref(a, qi, g, outsider_bound(u.d5, region));
         }
     }
+    LV_TL_END(3);
 }
 
 /*
@@ -247,6 +296,7 @@ __device__ __noinline__ void prepare_block(UpdateCtrl* c) {
 }
 
 __global__ void __launch_bounds__(kMeasureThreads, 4) lv_fit_kernel(const MeasureArgs a) {
+    LV_TL_SCHED();
     /* prologue on data written two or more kernels ago (flags, frame, iterate): runs while the searches finish */
     const int done = a.ctrl->done;
     /* with a.prep the grid has one extra block in front; it is dispatched first and is done long before
@@ -258,7 +308,7 @@ __global__ void __launch_bounds__(kMeasureThreads, 4) lv_fit_kernel(const Measur
         pdl_wait();
         pdl_trigger();
         /* the searches of this evaluation are over: reset their counters for the next one */
-        if (threadIdx.x < 3) a.hard_count[threadIdx.x] = 0u;
+        if (threadIdx.x < kCounters) a.hard_count[threadIdx.x] = 0u;
         return;
     }
 
@@ -282,6 +332,7 @@ __global__ void __launch_bounds__(kMeasureThreads, 4) lv_fit_kernel(const Measur
     }
     pdl_wait();                 /* the neighbour lists */
     pdl_trigger();
+    LV_TL_WORK(a.ctrl, 4);
     if (done) return;
 
     double acc = 0.0;
@@ -367,6 +418,7 @@ __global__ void __launch_bounds__(kMeasureThreads, 4) lv_fit_kernel(const Measur
     double* out = a.partials + (size_t)bid * kPartialStride;
     if (tid < 90) out[tid] = acc;
     if (tid == 90) out[90] = (double)count;
+    LV_TL_END(4);
 }
 
 /* ---- fixed-order reduction of the per-block partials ---------------------------------------- */
@@ -416,6 +468,7 @@ __global__ void __launch_bounds__(kStepThreads) lv_ieskf_step_kernel(UpdateCtrl*
                                                                      const double* partials, int n_partials) {
     /* before the wait: what the previous step (or begin) kernel left, two or more kernels ago */
     static_assert(kStepThreads >= 99 && 2 * kStepThreads >= kN * kN, "one pass for the state, two for P_j");
+    LV_TL_SCHED();
     const int t = threadIdx.x;
     const int done = c->done;
     double sv = 0.0;
@@ -425,6 +478,7 @@ __global__ void __launch_bounds__(kStepThreads) lv_ieskf_step_kernel(UpdateCtrl*
     if (t >= 96 && t < 99) cv = t == 96 ? c->n_evals : (t == 97 ? c->t : c->iter);
     pdl_wait();                 /* partials and the prepared P_j / dx_new of the fit kernel */
     pdl_trigger();
+    LV_TL_WORK(c, 5);
     if (done) return;
     __shared__ IeskfWork w;
     __shared__ double s_tmp[(kStepThreads / 32) * 96];
@@ -448,6 +502,7 @@ __global__ void __launch_bounds__(kStepThreads) lv_ieskf_step_kernel(UpdateCtrl*
     __syncthreads();
     LV_CK(2);
     ieskf_step(ex, prm, c, &w);
+    LV_TL_END(5);
 }
 
 __global__ void __launch_bounds__(kStepThreads) lv_reduce_partials_kernel(const double* partials, int n_partials,
@@ -464,7 +519,7 @@ __global__ void __launch_bounds__(kStepThreads) lv_reduce_partials_kernel(const 
 __global__ void __launch_bounds__(256) lv_ieskf_begin_kernel(UpdateCtrl* c, MeasureJob* job, const float* xyz, int n,
                                                              uint32_t* counters) {
     pdl_trigger();
-    if (counters && threadIdx.x < 3) counters[threadIdx.x] = 0u;    /* work-list lengths of the measurement kernels */
+    if (counters && threadIdx.x < kCounters) counters[threadIdx.x] = 0u;    /* work-list lengths of the measurement kernels */
     if (job && threadIdx.x == 0) {
         job->xyz = xyz;
         job->n = n;
@@ -555,7 +610,7 @@ cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st, cons
     const int sgrid = search_grid(a, group);
     /* work-list length, a spare word, redo-list length; inside an update with pdl the kernels
      * reset them themselves (begin kernel, fit kernel) so that every node of the update is a kernel */
-    if (!pdl) cudaMemsetAsync(a.hard_count, 0, 3 * sizeof(uint32_t), st);
+    if (!pdl) cudaMemsetAsync(a.hard_count, 0, kCounters * sizeof(uint32_t), st);
     if (reuse && a.ref) {
         if (probe) probe->at(probe->ctx, 4);
         launch_k(lv_reuse_kernel, (a.n + 127) / 128 > 0 ? (a.n + 127) / 128 : 1, 128, st, pdl != 0, a);
@@ -602,5 +657,21 @@ cudaError_t launch_l2_flush(void* buf, size_t bytes, cudaStream_t st) {
 #ifdef LV_STEP_TIMING
 extern "C" int lv_debug_step_clocks(long long* out) {
     return (int)cudaMemcpyFromSymbol(out, g_step_clk, sizeof(long long) * 64);
+}
+extern "C" int lv_debug_probes(unsigned long long* out) {
+    cudaDeviceSynchronize();
+    int e = (int)cudaMemcpyFromSymbol(out, g_probes, sizeof(unsigned long long) * 2);
+    unsigned long long z[2] = {0, 0};
+    cudaMemcpyToSymbol(g_probes, z, sizeof(z));
+    return e;
+}
+/* out[5][8][8]; resets the table (starts to ~0, ends to 0) */
+extern "C" int lv_debug_timeline(unsigned long long* out) {
+    cudaDeviceSynchronize();
+    int e = (int)cudaMemcpyFromSymbol(out, g_tl, sizeof(unsigned long long) * 320);
+    unsigned long long init[320];
+    for (int i = 0; i < 64; ++i) { init[i] = ~0ull; init[64 + i] = ~0ull; init[128 + i] = 0ull; init[192 + i] = 0ull; init[256 + i] = 0ull; }
+    cudaMemcpyToSymbol(g_tl, init, sizeof(init));
+    return e;
 }
 #endif

@@ -46,6 +46,10 @@ struct uint4 { unsigned int x, y, z, w; };
 #define LV_UNROLL_N(n)
 #endif
 
+#ifndef LV_PROBE_COUNT
+#define LV_PROBE_COUNT()      /* tuning build: counts hash probes */
+#endif
+
 namespace lv {
 
 enum { kMaxLevels = 4 };
@@ -133,6 +137,7 @@ LV_HD int voxel_find(const VoxelLevel& L, uint64_t key, uint32_t* start, uint32_
     uint32_t slot = voxel_hash(key) & L.mask;
     for (;;) {
         const uint4 e = load_slot(L.table + 2 * (size_t)slot);
+        LV_PROBE_COUNT();
         if (e.x == klo && e.y == khi) { *start = e.z; *count = e.w; return (int)slot; }
         if ((e.x & e.y) == 0xFFFFFFFFu) { *count = 0; return -1; }
         slot = (slot + 1) & L.mask;
