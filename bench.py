@@ -214,6 +214,8 @@ def run_native(args, rank, local_rank, world_size):
     prm = lv.params_from_yaml(os.path.join(lv.CONFIG_DIR, "xaloc.yaml"), device=local_rank,
                               max_map_points=MAP_POINTS + 4 * RINGS * AZIMUTHS, max_points=RINGS * AZIMUTHS,
                               stream=stream.cuda_stream)
+    if args.voxel:                                                  # tuning runs only; the default is the library's
+        prm.voxel_size = args.voxel
     world, mp, sweeps, x_props, truths = make_scene(lv, rank, prm=prm)
     n = sweeps[0].shape[0]
     loc = lv.Localizer(prm)
@@ -472,6 +474,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--voxel", type=float, default=0.0, help="tuning: finest voxel edge of the map (0 = library default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -135,13 +135,17 @@ LV_HD float4 load_point(const float4* p) {
 LV_HD int voxel_find(const VoxelLevel& L, uint64_t key, uint32_t* start, uint32_t* count) {
     const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
     uint32_t slot = voxel_hash(key) & L.mask;
-    for (;;) {
+    /* tables are built with load <= 0.6, so a probe sequence meets an empty slot long before it wraps; the bound
+     * only guarantees termination whatever the table holds */
+    for (uint32_t probes = 0; probes <= L.mask; ++probes) {
         const uint4 e = load_slot(L.table + 2 * (size_t)slot);
         LV_PROBE_COUNT();
         if (e.x == klo && e.y == khi) { *start = e.z; *count = e.w; return (int)slot; }
-        if ((e.x & e.y) == 0xFFFFFFFFu) { *count = 0; return -1; }
+        if ((e.x & e.y) == 0xFFFFFFFFu) break;
         slot = (slot + 1) & L.mask;
     }
+    *count = 0;
+    return -1;
 }
 
 /* ascending top-5 kept in registers.  id = position in the scanned array (-1 = none). */
