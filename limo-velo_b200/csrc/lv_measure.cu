@@ -18,6 +18,7 @@
  * Bound: HBM/L2 gather latency: algorithmic traffic is 72 B per point (12 B query +
  * 5 x 12 B neighbours), no tensor-core-shaped work.
  */
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -620,10 +621,14 @@ cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st, cons
         if (probe) probe->at(probe->ctx, 0);
         launch_search<false>(a, group, sgrid, st, pdl != 0);
     }
+    static const bool dbg_sync = getenv("LV_DEBUG_SYNC") != nullptr;   /* diagnosis: name the kernel that does not finish */
+    if (dbg_sync) { cudaStreamSynchronize(st); fprintf(stderr, "[lv] search done\n"); fflush(stderr); }
     if (probe) probe->at(probe->ctx, 1);
     launch_k(lv_search_upper_kernel, 148 * 8, 128, st, pdl != 0, a);
+    if (dbg_sync) { cudaStreamSynchronize(st); fprintf(stderr, "[lv] search-upper done\n"); fflush(stderr); }
     if (probe) probe->at(probe->ctx, 2);
     launch_k(lv_fit_kernel, grid + (a.prep ? 1 : 0), kMeasureThreads, st, pdl != 0, a);
+    if (dbg_sync) { cudaStreamSynchronize(st); fprintf(stderr, "[lv] fit done\n"); fflush(stderr); }
     if (probe) probe->at(probe->ctx, 3);
     return cudaGetLastError();
 }
