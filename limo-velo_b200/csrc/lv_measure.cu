@@ -1,5 +1,5 @@
 /*
- * lv_measure.cu — K1..K4 fused: one h-evaluation of the measurement model on the GPU.
+ * lv_measure.cu — the kernels of one h-evaluation of the measurement model and of the IESKF step.
  *
  * Replaces, per input point, the chain (reference paths relative to the LIMO-Velo tree)
  *   Mapper::match                 src/Modules/Mapper.cpp:40-56       world transform
@@ -7,16 +7,20 @@
  *   Plane::Plane / estimate_plane src/Objects/Plane.cpp:19-55, src/Utils/Utils.cpp:32-66
  *   Match::Match                  src/Objects/Match.cpp:18-22
  *   Localizator::calculate_H      src/Modules/Localizator.cpp:29-57
- * and the reduction IKFoM performs on its output,
+ * the reduction IKFoM performs on its output,
  *   HTH = h_x^T h_x, h_x^T h      esekfom.hpp:1723,1727
- * Two kernels per evaluation: K1 lv_search_kernel (exact 5-NN, thin, maximum occupancy) hands 24 B
- * per query (neighbour positions + 5th distance) to K2 lv_fit_kernel (plane fit, row, reduction).
- * H (Nm x 12 fp64) is never materialised: every thread produces its row in registers, rows are
- * staged once in shared memory and folded into the 78 + 12 unique sums per block, in a fixed
- * order (deterministic).
+ * and the 23x23 algebra between two evaluations (esekfom.hpp:1647-1817, csrc/lv_ieskf.h).
  *
- * Bound: HBM/L2 gather latency: algorithmic traffic is 72 B per point (12 B query +
- * 5 x 12 B neighbours), no tensor-core-shaped work.
+ * Kernels of one evaluation: lv_reuse_kernel (evaluations after the first: keep the neighbours the
+ * exact search provably returns again), lv_search_kernel (exact 5-NN at level 0, thin, 4 lanes per query),
+ * lv_search_upper_kernel (the queries level 0 cannot certify, one warp each), lv_fit_kernel (plane fit, Jacobian
+ * row, the 78 + 12 unique normal-equation sums per block in a fixed order; one spare block runs ieskf_prepare),
+ * lv_ieskf_step_kernel (one block: reduction of the partials, gain, dx, next frame, loop control).  H (Nm x 12
+ * fp64) is never materialised.  Inside an update every kernel is launched with programmatic dependent launch and
+ * the whole update is replayed as one CUDA graph (lv_capi.cu).
+ *
+ * Bound: L2 / HBM gather LATENCY, not bandwidth (algorithmic traffic 72 B per point: 12 B query + 5 x 12 B
+ * neighbours); no tensor-core-shaped work.
  */
 #include <stdio.h>
 #include <stdlib.h>
