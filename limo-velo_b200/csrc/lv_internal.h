@@ -28,7 +28,7 @@ struct MeasureJob {
     int32_t n_tiles;
 };
 
-/* per-launch constants of the fused measure kernel */
+/* per-launch constants of the measurement kernels (reuse, search, search-upper, fit) */
 struct MeasureArgs {
     const float* xyz;          /* n x 3 packed, LiDAR frame                               */
     int32_t n;                 /* with `job`: the capacity the grids were sized for       */
