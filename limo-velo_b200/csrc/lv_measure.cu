@@ -82,8 +82,13 @@ static void init_pairs() {
  * the predecessor writes.  Every path through a kernel executes pdl_wait() and triggers only AFTER it, so
  * "this kernel runs past its wait" implies "its predecessor is complete", and a prologue may read whatever
  * was written two or more kernels ago.  Without the launch attribute both are no-ops. */
+#ifdef LV_NO_GRIDDEP   /* diagnosis build: without the instructions every launch must be a plain one (LV_NO_PDL=1) */
+__device__ __forceinline__ void pdl_wait() {}
+__device__ __forceinline__ void pdl_trigger() {}
+#else
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 /* the sweep of this launch: kernel arguments, or the device-side job of a graph replay */
 struct JobView { const float* xyz; int n; int n_tiles; };
