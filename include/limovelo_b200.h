@@ -234,6 +234,28 @@ lv_status lv_voxelgrid_downsample(lv_handle h, const float* xyz, int64_t n, floa
 lv_status lv_voxelgrid_downsample_device(lv_handle h, const float* d_xyz, int64_t n, float downsample_prec,
                                          float* d_xyz_out, int64_t* n_out);
 
+/* ---- wire format of the LiDAR message (last item) --------------------------------------
+ * PointCloudProcessor::msg2points (src/Utils/PointCloudProcessor.cpp:24-99) on the raw `data` of a
+ * sensor_msgs/PointCloud2: the point structs of include/Headers/Common.hpp:109-221 are read field by field at the
+ * byte offsets the message declares (pcl::fromROSMsg maps fields by name), so no ROS / PCL type is needed here. */
+typedef enum lv_lidar_type { LV_LIDAR_VELODYNE = 0, LV_LIDAR_HESAI = 1, LV_LIDAR_OUSTER = 2, LV_LIDAR_CUSTOM = 3 } lv_lidar_type;
+typedef struct lv_cloud_layout {
+    int32_t point_step;        /* bytes per point */
+    int32_t off_x, off_y, off_z;           /* float32 */
+    int32_t off_intensity;     /* velodyne / custom: float32 `intensity`; hesai: uint8 `intensity`; ouster: uint16 `reflectivity` */
+    int32_t off_time;          /* velodyne: float32 `time`; hesai / custom: float64 `timestamp`; ouster: uint32 `t` (ns) */
+    int32_t off_range;         /* ouster: uint32 `range`; others: unused (range = |p|, Point.cpp:166-169) */
+} lv_cloud_layout;
+/* the time semantics of the YAML (Common.hpp:56-107): stamp_beginning, offset_beginning, full_rotation_time.
+ * header_stamp_us = pcl header stamp (microseconds).  Outputs (n entries each; intensity / range may be NULL):
+ * xyz, absolute time per point (Point.cpp:37-111 + get_begin_time, PointCloudProcessor.cpp:42-88), intensity, range. */
+lv_status lv_pointcloud2_to_points(lv_lidar_type type, const lv_cloud_layout* layout, const uint8_t* data, int64_t n,
+                                   uint64_t header_stamp_us, int stamp_beginning, int offset_beginning,
+                                   double full_rotation_time, float* xyz, double* time, float* intensity, float* range);
+/* PointCloudProcessor::sort_points (PointCloudProcessor.cpp:114-123): order of the points by time (stable; the
+ * reference's std::sort leaves equal stamps in unspecified order)                                          */
+lv_status lv_time_sort_indices(const double* time, int64_t n, int32_t* idx_out);
+
 /* ---- synthetic reader (replaces the ROS subscribers of src/main.cpp:27-39) ---- */
 typedef struct lv_synth_world lv_synth_world;
 /* seeded "city-block" world whose surface sampling holds exactly m map points              */

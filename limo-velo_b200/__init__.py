@@ -236,6 +236,38 @@ def compensator_get_t2(path, t2):
     return out
 
 
+class CloudLayout(C.Structure):
+    _fields_ = [("point_step", C.c_int32), ("off_x", C.c_int32), ("off_y", C.c_int32), ("off_z", C.c_int32),
+                ("off_intensity", C.c_int32), ("off_time", C.c_int32), ("off_range", C.c_int32)]
+
+
+LIDAR_TYPES = {"velodyne": 0, "hesai": 1, "ouster": 2, "custom": 3}
+
+
+def pointcloud2_to_points(lidar, pts, header_stamp_us, stamp_beginning, offset_beginning, full_rotation_time):
+    """PointCloudProcessor::msg2points on a numpy structured array (its buffer is the message's `data`)"""
+    pts = np.ascontiguousarray(pts)
+    f = pts.dtype.fields
+    tname = {"velodyne": "time", "ouster": "t"}.get(lidar, "timestamp")
+    iname = "reflectivity" if lidar == "ouster" else "intensity"
+    lay = CloudLayout(pts.dtype.itemsize, f["x"][1], f["y"][1], f["z"][1], f[iname][1], f[tname][1],
+                      f["range"][1] if "range" in f else 0)
+    n = len(pts)
+    xyz, t = np.zeros((n, 3), np.float32), np.zeros(n, np.float64)
+    inten, rng = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    _check(lib().lv_pointcloud2_to_points(LIDAR_TYPES[lidar], C.byref(lay), pts.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_int64(n),
+                                         C.c_uint64(header_stamp_us), int(stamp_beginning), int(offset_beginning),
+                                         C.c_double(full_rotation_time), _f(xyz), _d(t), _f(inten), _f(rng)))
+    return xyz, t, inten, rng
+
+
+def time_sort_indices(t):
+    t = np.ascontiguousarray(t, np.float64)
+    idx = np.zeros(len(t), np.int32)
+    _check(lib().lv_time_sort_indices(_d(t), C.c_int64(len(t)), idx.ctypes.data_as(C.POINTER(C.c_int32))))
+    return idx
+
+
 def init_state_host(params, q_imu=(0, 0, 0, 1)):
     """Localizator::init_IKFoM_state on the host (no GPU needed)."""
     x, P = np.zeros(STATE_LEN), np.zeros((DOF, DOF))

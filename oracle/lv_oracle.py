@@ -395,3 +395,41 @@ def voxelgrid_downsample(xyz, leaf):
     if n < 0:
         raise ValueError("leaf size too small for the extent of the cloud (PCL refuses)")
     return out[:n]
+
+
+# ---- wire format (numpy restatement of PointCloudProcessor::msg2points, no C involved) ------------------
+def _us2s(t):      # Conversions::microsec2Sec (Utils.cpp:18-23): int quotient + int remainder * 1e-6
+    t = int(t)
+    return float(int(t // 1000000) + int(t % 1000000) * 1e-6)
+
+
+def _ns2s(t):      # Conversions::nanosec2Sec (Utils.cpp:25-30)
+    t = np.asarray(t, dtype=np.int64)
+    return (t // 1000000000).astype(np.float64) + (t % 1000000000).astype(np.float64) * 1e-9
+
+
+def pointcloud2_to_points(lidar, pts, header_stamp_us, stamp_beginning, offset_beginning, full_rotation_time):
+    """pts: numpy structured array with the fields of the reference's point struct (Common.hpp:109-221):
+    velodyne x y z intensity time | hesai x y z intensity(u1) timestamp | ouster x y z t(u4) reflectivity(u2) range(u4) |
+    custom x y z intensity timestamp.  Returns xyz (n,3) f32, time (n,) f64, intensity f32, range f32."""
+    xyz = np.stack([pts["x"], pts["y"], pts["z"]], axis=1).astype(np.float32)
+    nrm = np.sqrt((xyz[:, 0] * xyz[:, 0] + xyz[:, 1] * xyz[:, 1]) + xyz[:, 2] * xyz[:, 2]).astype(np.float32)
+    if lidar == "velodyne":
+        raw = pts["time"].astype(np.float64)
+    elif lidar == "ouster":
+        raw = _ns2s(pts["t"])
+    else:
+        raw = pts["timestamp"].astype(np.float64)
+    begin = 0.0
+    if lidar in ("velodyne", "ouster") and len(pts):
+        begin = _us2s(header_stamp_us) + raw[0] if stamp_beginning else _us2s(header_stamp_us) + raw[0] - raw[-1]
+        t = raw if offset_beginning else full_rotation_time + raw
+    else:
+        t = raw
+    t = t + begin
+    if lidar == "ouster":
+        inten, rng = pts["reflectivity"].astype(np.float32), pts["range"].astype(np.float32)
+    else:
+        inten, rng = pts["intensity"].astype(np.float32), nrm
+    return xyz, t, inten, rng
+
