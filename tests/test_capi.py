@@ -48,6 +48,18 @@ def test_argument_errors(lv):
     assert L.lv_create(C.byref(p), C.byref(h)) == lv.ERR_ARG
     assert L.lv_map_size(None) == 0 and L.lv_map_exists(None) == 0
     assert L.lv_params_from_yaml(b"/nonexistent.yaml", C.byref(p)) == lv.ERR_IO
+    # the widened boundary (deskew, downsamplers, wire format): null handle / null buffers are argument errors, not crashes
+    n_out = C.c_int64(7)
+    assert L.lv_compensate(None, None, 0, None, None, None, C.c_int64(0), None) == lv.ERR_ARG
+    assert L.lv_compensate_device(None, None, 0, None, None, None, C.c_int64(0), None) == lv.ERR_ARG
+    assert L.lv_voxelgrid_downsample(None, None, C.c_int64(0), C.c_float(0.5), None, C.byref(n_out)) == lv.ERR_ARG
+    assert L.lv_temporal_downsample(None, None, C.c_int64(0), 4, C.c_double(4.0), None, None, C.byref(n_out)) == lv.ERR_ARG
+    assert L.lv_pointcloud2_to_points(0, None, None, C.c_int64(0), C.c_uint64(0), 0, 1, C.c_double(0.1), None, None, None, None) == lv.ERR_ARG
+    lay = lv.CloudLayout(16, 0, 4, 8, 12, 12, 0)
+    buf = (C.c_uint8 * 16)()
+    xyz, t = (C.c_float * 3)(), (C.c_double * 1)()
+    assert L.lv_pointcloud2_to_points(9, C.byref(lay), buf, C.c_int64(1), C.c_uint64(0), 0, 1, C.c_double(0.1), xyz, t, None, None) == lv.ERR_ARG
+    assert L.lv_time_sort_indices(None, C.c_int64(0), None) == lv.ERR_ARG
 
 
 def test_yaml_reader_matches_pyyaml(lv):
