@@ -32,30 +32,97 @@ RINGS, AZIMUTHS = 64, 1024           # Velodyne-64 pattern: 65 536 beams
 N_SWEEPS = 8                          # distinct sweeps along the road, replayed round-robin
 ALGO_BYTES_PER_POINT = 72             # 12 B query + 5 x 12 B neighbours
 
+# BASELINE.json `configs` (SURVEY.md 8d "concrete synthetic inputs").  The driver's line is cfg1 (the config the
+# metric is quoted on); the others are run with --config and land in profiles/bench_<cfg>.json.
+#   sub_sweeps  a sweep is cut into this many consecutive pieces (firing order = time order), one update each
+#               (kitti.yaml: delta 0.01 s -> 10 updates per 0.1 s rotation, README.md:14)
+#   max_iters   MAX_NUM_ITERS override (cfg0: a single h-evaluation)
+#   planar      ground-only map (BASELINE.json configs[0])
+CONFIGS = {
+    "cfg0": dict(yaml="xaloc.yaml", map_points=100_000, rings=64, azimuths=1024, elev=(-24.8, 2.0), sub_sweeps=1,
+                 max_iters=0, planar=True, seed_off=0,
+                 what="single 64k-pt Velodyne sweep vs 100k-pt planar map, 1 evaluation"),
+    "cfg1": dict(yaml="xaloc.yaml", map_points=MAP_POINTS, rings=RINGS, azimuths=AZIMUTHS, elev=(-24.8, 2.0), sub_sweeps=1,
+                 max_iters=None, planar=False, seed_off=1,
+                 what="xaloc.yaml, 65536-pt Velodyne-64 sweep vs 1000000-pt map, MAX_NUM_ITERS=3 (<=4 evaluations)"),
+    "cfg2": dict(yaml="kitti.yaml", map_points=5_000_000, rings=64, azimuths=2048, elev=(-24.8, 2.0), sub_sweeps=10,
+                 max_iters=None, planar=False, seed_off=2,
+                 what="kitti.yaml, 131072-pt sweeps cut into 10 sub-sweeps of 13107 pts (delta 0.01 s) vs 5M-pt map"),
+    "cfg3": dict(yaml="ouster.yaml", map_points=10_000_000, rings=128, azimuths=2048, elev=(-22.5, 22.5), sub_sweeps=1,
+                 max_iters=None, planar=False, seed_off=3,
+                 what="ouster.yaml, 262144-pt Ouster-128 sweep vs 10M-pt map"),
+}
 
-def workload_config(n_gpus):
-    return {"workload": "cfg1: xaloc.yaml, %d-pt Velodyne-64 sweep vs %d-pt map, MAX_NUM_ITERS=3 (<=4 evaluations)"
-                        % (RINGS * AZIMUTHS, MAP_POINTS),
-            "sweep_points": RINGS * AZIMUTHS, "map_points": MAP_POINTS, "yaml": "xaloc.yaml",
-            "sequences": n_gpus, "parallelism": "one independent sequence per GPU (no data-path collective)",
+
+def metric_name(cfg):
+    return METRIC if cfg == "cfg1" else "matched-points/sec per IESKF iteration (%s: %s)" % (cfg, CONFIGS[cfg]["what"])
+
+
+def update_points(cfg):
+    c = CONFIGS[cfg]
+    return (c["rings"] * c["azimuths"]) // c["sub_sweeps"]
+
+
+def workload_config(n_gpus, cfg="cfg1", sequences=None):
+    c = CONFIGS[cfg]
+    return {"workload": "%s: %s" % (cfg, c["what"]),
+            "sweep_points": update_points(cfg), "map_points": c["map_points"], "yaml": c["yaml"],
+            "sequences": sequences if sequences is not None else n_gpus,
+            "parallelism": "one independent sequence per GPU (no data-path collective)",
             "l2": "flushed (256 MiB write) between timed steps; step time = CUDA events around each update"}
 
 
-def make_scene(lv, rank, n_sweeps=N_SWEEPS, prm=None):
-    """Seeded world + sweeps + predicted states for one sequence (seed base + 1 + rank: SURVEY 8d cfg1/cfg4)."""
+def config_params(lv, cfg, **over):
+    """lv_params of a config: its YAML + the capacities of its sizes (+ overrides)"""
+    c = CONFIGS[cfg]
+    n = update_points(cfg)
+    kw = dict(max_map_points=c["map_points"] + 4 * c["rings"] * c["azimuths"], max_points=n)
+    kw.update(over)
+    prm = lv.params_from_yaml(os.path.join(lv.CONFIG_DIR, c["yaml"]), **kw)
+    if c["max_iters"] is not None:
+        prm.MAX_NUM_ITERS = c["max_iters"]
+    return prm
+
+
+def make_scene(lv, rank, n_sweeps=N_SWEEPS, prm=None, cfg="cfg1"):
+    """Seeded world + updates (sweeps or sub-sweeps) + predicted states for one sequence
+    (seed base + seed_off + 10 * rank: SURVEY 8d cfg0..cfg4).  Returns world, map, updates, x_props, truths."""
     O = G.load_oracle()
-    world = lv.SynthWorld(SEED + 1 + 10 * rank, MAP_POINTS)
+    c = CONFIGS[cfg]
+    rng = np.random.default_rng(SEED + 1000 + rank + 100 * (c["seed_off"] - 1))
+    world = lv.SynthWorld(SEED + c["seed_off"] + 10 * rank, c["map_points"] if not c["planar"] else 6 * c["map_points"])
     mp = world.map()
-    rng = np.random.default_rng(SEED + 1000 + rank)
+    n_upd = update_points(cfg)
     sweeps, x_props, truths = [], [], []
+    if c["planar"]:
+        # ground-only map: the map_points ground samples closest to the road position of the sweeps; sweeps keep
+        # only the returns from that disc (ray-cast at 4x the azimuth density so that enough of them remain)
+        centre = world.pose(15.0, prm)[0:3]
+        ground = mp[mp[:, 2] < -1.6]
+        d2 = ((ground[:, :2] - centre[:2].astype(np.float32)) ** 2).sum(1)
+        keep = np.argsort(d2, kind="stable")[:c["map_points"]]
+        radius = float(np.sqrt(d2[keep[-1]]))
+        mp = np.ascontiguousarray(ground[np.sort(keep)])
     for i in range(n_sweeps):
         truth = world.pose(15.0 + 1.5 * i, prm)            # 15 m/s at 10 Hz
-        sweeps.append(world.sweep(truth, rings=RINGS, azimuths=AZIMUTHS, min_dist=4.0, range_sigma=0.02, seed=100 + i))
-        d = np.zeros(23)
-        d[0:3] = rng.uniform(-0.05, 0.05, 3)
-        d[3:6] = rng.uniform(-0.5, 0.5, 3) * np.pi / 180.0
-        x_props.append(O.boxplus(truth, d))
-        truths.append(truth)
+        if c["planar"]:
+            truth = world.pose(15.0 + 0.25 * i, prm)       # stay inside the disc
+            raw = world.sweep(truth, rings=c["rings"], azimuths=4 * c["azimuths"], elev=c["elev"], min_dist=4.0,
+                              range_sigma=0.02, seed=100 + i)
+            gw = world_points(raw, truth)
+            ok = (gw[:, 2] < -1.5) & (((gw[:, :2] - centre[:2].astype(np.float32)) ** 2).sum(1) < (radius - 1.0) ** 2)
+            sw = np.ascontiguousarray(raw[ok][:c["rings"] * c["azimuths"]])
+            assert len(sw) == c["rings"] * c["azimuths"], "planar scene: not enough ground returns (%d)" % len(sw)
+        else:
+            sw = world.sweep(truth, rings=c["rings"], azimuths=c["azimuths"], elev=c["elev"], min_dist=4.0,
+                             range_sigma=0.02, seed=100 + i)
+        for k in range(c["sub_sweeps"]):
+            sweeps.append(np.ascontiguousarray(sw[k * n_upd:(k + 1) * n_upd]))
+            d = np.zeros(23)
+            d[0:3] = rng.uniform(-0.05, 0.05, 3)
+            d[3:6] = rng.uniform(-0.5, 0.5, 3) * np.pi / 180.0
+            x_props.append(O.boxplus(truth, d))
+            truths.append(truth)
     return world, mp, sweeps, x_props, truths
 
 
@@ -153,8 +220,10 @@ def _cpu_leg(lv, prm, mp, sweeps, x_props, P0, budget_s, threads, max_updates=No
     """Time the CPU oracle (Localizator::correct restated; kNN = the reference's own ikd-Tree when
     oracle/_ref is present) on whole updates of the same workload until `budget_s` is used."""
     O = G.load_oracle()
-    kind = "reference" if O.ref_available() else "port"
-    om = O.Map(O.KNN_REF_IKDTREE if kind == "reference" else O.KNN_KDTREE)
+    # "reference-kNN+port": the 5-NN runs in the reference's own ikd_Tree.cpp (oracle/_ref, compiled verbatim); plane fit,
+    # Jacobian rows and the IESKF are the oracle's restatement (Eigen / IKFoM cannot be built in this image)
+    kind = "reference-kNN+port" if O.ref_available() else "port"
+    om = O.Map(O.KNN_REF_IKDTREE if kind != "port" else O.KNN_KDTREE)
     om.build(mp)
     om.knn(mp[0])                       # forces the lazy tree build of the port backend
     O.set_threads(threads)
@@ -176,17 +245,18 @@ def _cpu_leg(lv, prm, mp, sweeps, x_props, P0, budget_s, threads, max_updates=No
             break
     what = ("%d full updates (%d-pt sweep, %d-pt map, %d point-evaluations) in %.1f s; kNN = %s" %
             (n_upd, sweeps[0].shape[0], mp.shape[0], pts, secs,
-             "reference ikd_Tree.cpp compiled verbatim (oracle/_ref)" if kind == "reference" else "oracle kd-tree port"))
+             "reference ikd_Tree.cpp compiled verbatim (oracle/_ref)" if kind != "port" else "oracle kd-tree port"))
     return {"value": pts / secs, "unit": UNIT, "cores": threads, "kind": kind, "sample": what}, pts, secs, n_upd
 
 
 def run_reference(args, rank, world_size):
     if rank != 0:
         return
-    lv = G.load_package()
-    prm = lv.params_from_yaml(os.path.join(lv.CONFIG_DIR, "xaloc.yaml"))
+    lv = G.load_package()                    # the Python module only: this arm loads liblv_synth.so (inputs), never the CUDA library
+    cfg = args.config
+    prm = config_params(lv, cfg, _L=lv.synth_lib())
     O = G.load_oracle()
-    _, mp, sweeps, x_props, _ = make_scene(lv, 0, n_sweeps=4, prm=prm)
+    _, mp, sweeps, x_props, _ = make_scene(lv, 0, n_sweeps=4, prm=prm, cfg=cfg)
     x0, P0 = O.init_state(initial_gravity=prm.initial_gravity[:], I_Rotation_L=prm.I_Rotation_L[:],
                           I_Translation_L=prm.I_Translation_L[:])
     ncores = os.cpu_count() or 1
@@ -194,13 +264,14 @@ def run_reference(args, rank, world_size):
     cpu_leg(lv, prm, mp, sweeps, x_props, P0, 0, threads, max_updates=max(1, args.warmup if args.warmup < 2 else 1))
     # one step = one full update (~0.16 s with the reference's 3-thread team); K steps, but never more than ~3 minutes
     base, pts, secs, n_upd = cpu_leg(lv, prm, mp, sweeps, x_props, P0, 170.0, threads, max_updates=args.steps)
-    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": metric_name(cfg), "value": base["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": n_upd, "steps_requested": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / n_upd,
             "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 geometry / f64 Jacobian+filter", "data": "synthetic",
-            "config": workload_config(args.gpus), "cpu_baseline": base,
+            "config": workload_config(args.gpus, cfg, sequences=1), "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "host_cpu_count": ncores}
+            "gpu_launches": 0, "host_cpu_count": ncores,
+            "product_library_loaded": any("liblimovelo_b200" in l for l in open("/proc/self/maps"))}
     print(json.dumps(line), flush=True)
 
 
@@ -215,12 +286,11 @@ def run_native(args, rank, local_rank, world_size):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.Stream()            # a real (non-default) stream: the library launches on it
     torch.cuda.set_stream(stream)
-    prm = lv.params_from_yaml(os.path.join(lv.CONFIG_DIR, "xaloc.yaml"), device=local_rank,
-                              max_map_points=MAP_POINTS + 4 * RINGS * AZIMUTHS, max_points=RINGS * AZIMUTHS,
-                              stream=stream.cuda_stream)
+    cfg = args.config
+    prm = config_params(lv, cfg, device=local_rank, stream=stream.cuda_stream)
     if args.voxel:                                                  # tuning runs only; the default is the library's
         prm.voxel_size = args.voxel
-    world, mp, sweeps, x_props, truths = make_scene(lv, rank, prm=prm)
+    world, mp, sweeps, x_props, truths = make_scene(lv, rank, prm=prm, cfg=cfg)
     n = sweeps[0].shape[0]
     loc = lv.Localizer(prm)
     loc.map_build(mp)
@@ -408,10 +478,10 @@ def run_native(args, rank, local_rank, world_size):
             cpu, _, _, _ = cpu_leg(lv, prm, mp, sweeps, x_props, P0, args.cpu_seconds, 1)
         sz_ctrl = loc.result_bytes()
         line = {
-            "metric": METRIC, "value": pts_all / (step_ms_max * 1e-3), "unit": UNIT, "n_gpus": world_size,
+            "metric": metric_name(cfg), "value": pts_all / (step_ms_max * 1e-3), "unit": UNIT, "n_gpus": world_size,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 geometry / f64 Jacobian+filter", "data": "synthetic", "config": workload_config(world_size),
+            "dtype": "f32 geometry / f64 Jacobian+filter", "data": "synthetic", "config": workload_config(world_size, cfg),
             "evaluations_per_step": evals / args.steps, "accept_rate": matched_all / max(1.0, pts_all),
             "matched_points_per_s": matched_all / (step_ms_max * 1e-3),
             "wall_ms_total_incl_flush_and_readback": 1e3 * t_wall,
@@ -478,6 +548,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--config", default="cfg1", choices=sorted(CONFIGS), help="BASELINE.json config (default cfg1 = the metric's)")
     ap.add_argument("--voxel", type=float, default=0.0, help="tuning: finest voxel edge of the map (0 = library default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -256,21 +256,6 @@ lv_status lv_pointcloud2_to_points(lv_lidar_type type, const lv_cloud_layout* la
  * reference's std::sort leaves equal stamps in unspecified order)                                          */
 lv_status lv_time_sort_indices(const double* time, int64_t n, int32_t* idx_out);
 
-/* ---- synthetic reader (replaces the ROS subscribers of src/main.cpp:27-39) ---- */
-typedef struct lv_synth_world lv_synth_world;
-/* seeded "city-block" world whose surface sampling holds exactly m map points              */
-lv_synth_world* lv_synth_world_create(uint64_t seed, int64_t m);
-void lv_synth_world_destroy(lv_synth_world* w);
-int64_t lv_synth_world_map(const lv_synth_world* w, float* xyz_out, int64_t cap);
-double lv_synth_world_extent(const lv_synth_world* w);
-/* pose of the sensor platform at arc-length s along the world's road (state layout above)   */
-void lv_synth_pose(const lv_synth_world* w, double s, const lv_params* p, double* x_out);
-/* ray-cast one sweep of `rings` x `azimuths` beams (elevations elev_lo..elev_hi degrees)
- * from state x; writes exactly rings*azimuths points in the LiDAR frame, firing order.       */
-int64_t lv_synth_sweep(const lv_synth_world* w, const double* x, int rings, int azimuths,
-                       double elev_lo_deg, double elev_hi_deg, double min_dist, double range_sigma,
-                       uint64_t seed, float* xyz_out);
-
 #ifdef __cplusplus
 }
 #endif

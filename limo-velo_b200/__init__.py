@@ -15,7 +15,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblimovelo_b200.so")
+LIB_PATH = os.environ.get("LV_LIB_PATH") or os.path.join(_HERE, "liblimovelo_b200.so")   # LV_LIB_PATH: variant builds of tools/
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "limovelo_b200.h")
 
 STATE_LEN, DOF, MAX_EVALS = 26, 23, 8
@@ -118,6 +118,28 @@ def lib():
     L.lv_profile_enable.argtypes = [vp, C.c_int]
     L.lv_profile_get.argtypes = [vp, C.POINTER(Profile), C.c_int]
     L.lv_flush_l2.argtypes = [vp]
+    _lib = L
+    return L
+
+
+SYNTH_LIB_PATH = os.path.join(_HERE, "liblv_synth.so")
+_synth = None
+
+
+def synth_lib():
+    """liblv_synth.so (include/lv_synth.h): the synthetic reader + the YAML reader, plain C++ — a process that only
+    needs inputs (bench.py's CPU reference arm) never loads the CUDA library."""
+    global _synth
+    if _synth is not None:
+        return _synth
+    if not os.path.exists(SYNTH_LIB_PATH):
+        raise RuntimeError("liblv_synth.so is not built (run __graft_entry__.build())")
+    L = C.CDLL(SYNTH_LIB_PATH)
+    dp, fp, vp, i64 = C.POINTER(C.c_double), C.POINTER(C.c_float), C.c_void_p, C.c_int64
+    L.lv_default_params.argtypes = [C.POINTER(Params)]
+    L.lv_default_params.restype = None
+    L.lv_params_from_yaml.argtypes = [C.c_char_p, C.POINTER(Params)]
+    L.lv_init_state_host.argtypes = [C.POINTER(Params), fp, dp, dp]
     L.lv_synth_world_create.argtypes = [C.c_uint64, i64]
     L.lv_synth_world_create.restype = vp
     L.lv_synth_world_destroy.argtypes = [vp]
@@ -131,7 +153,7 @@ def lib():
     L.lv_synth_sweep.argtypes = [vp, dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                  C.c_uint64, fp]
     L.lv_synth_sweep.restype = i64
-    _lib = L
+    _synth = L
     return L
 
 
@@ -143,9 +165,9 @@ def _d(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def default_params(**over):
+def default_params(_L=None, **over):
     p = Params()
-    lib().lv_default_params(C.byref(p))
+    (_L or lib()).lv_default_params(C.byref(p))
     for k, v in over.items():
         cur = getattr(p, k)
         if hasattr(cur, "__len__"):
@@ -156,9 +178,11 @@ def default_params(**over):
     return p
 
 
-def params_from_yaml(path, **over):
-    p = default_params()
-    st = lib().lv_params_from_yaml(str(path).encode(), C.byref(p))
+def params_from_yaml(path, _L=None, **over):
+    """lv_params from a LIMO-Velo YAML (+ field overrides).  _L: the library providing the reader (default: the product's;
+    liblv_synth.so carries the same reader for processes that must not load the CUDA library)"""
+    p = default_params(_L)
+    st = (_L or lib()).lv_params_from_yaml(str(path).encode(), C.byref(p))
     if st != OK:
         raise RuntimeError("lv_params_from_yaml(%s) -> %s" % (path, STATUS_NAMES[st]))
     for k, v in over.items():
@@ -497,10 +521,10 @@ class PinnedBuffer:
 
 
 class SynthWorld:
-    """Seeded synthetic world + LiDAR ray caster (host C++, limo-velo_b200/host/lv_synth.cpp)."""
+    """Seeded synthetic world + LiDAR ray caster (liblv_synth.so, limo-velo_b200/host/lv_synth.cpp)."""
 
     def __init__(self, seed, m):
-        self.L = lib()
+        self.L = synth_lib()
         self.w = self.L.lv_synth_world_create(int(seed), int(m))
         if not self.w:
             raise RuntimeError("lv_synth_world_create failed")

@@ -49,6 +49,22 @@ struct uint4 { unsigned int x, y, z, w; };
 #ifndef LV_PROBE_COUNT
 #define LV_PROBE_COUNT()      /* tuning build: counts hash probes */
 #endif
+/* diagnosis build (-DLV_WATCHDOG, tools/diag_hang.sh): every data-dependent loop of the search counts its trips and,
+ * past a bound no legitimate input reaches, records (loop id, two values) once and leaves the loop */
+#if defined(LV_WATCHDOG) && defined(LV_WATCHDOG_TU) && defined(__CUDA_ARCH__)   /* g_lv_wd: defined by the including .cu */
+#define LV_WD_INIT() uint32_t lv_wd_n_ = 0
+#define LV_WD(id, a, b)                                                                                   \
+    if (++lv_wd_n_ > 4000000u) {                                                                          \
+        if (atomicCAS(&g_lv_wd[0], 0ull, (unsigned long long)(id)) == 0ull) {                              \
+            g_lv_wd[1] = (unsigned long long)(a); g_lv_wd[2] = (unsigned long long)(b);                    \
+            g_lv_wd[3] = blockIdx.x; g_lv_wd[4] = threadIdx.x;                                             \
+        }                                                                                                 \
+        break;                                                                                            \
+    }
+#else
+#define LV_WD_INIT()
+#define LV_WD(id, a, b)
+#endif
 
 namespace lv {
 
@@ -137,7 +153,9 @@ LV_HD int voxel_find(const VoxelLevel& L, uint64_t key, uint32_t* start, uint32_
     uint32_t slot = voxel_hash(key) & L.mask;
     /* tables are built with load <= 0.6, so a probe sequence meets an empty slot long before it wraps; the bound
      * only guarantees termination whatever the table holds */
+    LV_WD_INIT();
     for (uint32_t probes = 0; probes <= L.mask; ++probes) {
+        LV_WD(1, key, L.mask)
         const uint4 e = load_slot(L.table + 2 * (size_t)slot);
         LV_PROBE_COUNT();
         if (e.x == klo && e.y == khi) { *start = e.z; *count = e.w; return (int)slot; }
@@ -337,13 +355,16 @@ LV_HD bool level0_scan(const VoxelMapView& m, float gx, float gy, float gz, floa
         uint32_t j = (uint32_t)Grp::lane();
         /* eight, then four independent 16-byte loads in flight per lane: a typical bucket (~56 points over 4 lanes)
          * takes two round trips instead of four (K1 is latency-bound: -11 % with the 8-wide step) */
+        LV_WD_INIT();
         for (; j + 7 * step < n; j += 8 * step) {
+            LV_WD(2, bstart, bcount)
             float4 q[8];
             LV_UNROLL_N(8) for (int u = 0; u < 8; ++u) q[u] = load_point(p + j + (uint32_t)u * step);
             LV_UNROLL_N(8) for (int u = 0; u < 8; ++u)
                 top5_insert(loc, sq_dist(gx, gy, gz, q[u].x, q[u].y, q[u].z), (int)(bstart + j + (uint32_t)u * step));
         }
         for (; j + 3 * step < n; j += 4 * step) {   /* four independent 16-byte loads in flight per lane */
+            LV_WD(3, bstart, bcount)
             const float4 q0 = load_point(p + j), q1 = load_point(p + j + step), q2 = load_point(p + j + 2 * step),
                          q3 = load_point(p + j + 3 * step);
             top5_insert(loc, sq_dist(gx, gy, gz, q0.x, q0.y, q0.z), (int)(bstart + j));
@@ -352,6 +373,7 @@ LV_HD bool level0_scan(const VoxelMapView& m, float gx, float gy, float gz, floa
             top5_insert(loc, sq_dist(gx, gy, gz, q3.x, q3.y, q3.z), (int)(bstart + j + 3 * step));
         }
         for (; j < n; j += step) {
+            LV_WD(4, bstart, bcount)
             const float4 q = load_point(p + j);
             top5_insert(loc, sq_dist(gx, gy, gz, q.x, q.y, q.z), (int)(bstart + j));
         }
@@ -433,7 +455,9 @@ LV_HD void knn5_upper(const VoxelMapView& m, float gx, float gy, float gz, float
         }
         const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
         const uint32_t excl = incl - cnt;
+        LV_WD_INIT();
         for (uint32_t j0 = 0; j0 < total; j0 += 128) {           /* four independent loads in flight per lane */
+            LV_WD(5, total, l)
             uint32_t idx[4];
             bool ok[4];
 #pragma unroll

@@ -11,6 +11,7 @@
 
 #include <chrono>
 
+#include "../../include/lv_synth.h"
 #include "Modules.hpp"
 
 int main(int argc, char** argv) {

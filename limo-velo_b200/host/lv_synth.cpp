@@ -21,7 +21,7 @@
 #include <algorithm>
 #include <vector>
 
-#include "../../include/limovelo_b200.h"
+#include "../../include/lv_synth.h"
 #include "../csrc/lv_host.h"
 #include "../csrc/lv_manifold.h"
 

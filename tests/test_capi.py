@@ -23,6 +23,23 @@ def test_library_exports_every_declared_symbol(lv):
     assert b"limovelo_b200" in L.lv_version()
 
 
+def test_synth_library_exports_every_declared_symbol_and_is_cuda_free(lv):
+    """include/lv_synth.h <-> liblv_synth.so; the product library no longer carries the synthetic reader, and the
+    synthetic reader does not pull in the CUDA runtime (bench.py's CPU reference arm loads only this one)"""
+    header = open(os.path.join(os.path.dirname(lv.HEADER_PATH), "lv_synth.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    names = set(re.findall(r"\b(lv_[a-z0-9_]+)\s*\(", body))
+    assert len(names) >= 6
+    S = C.CDLL(lv.SYNTH_LIB_PATH)
+    assert [n for n in sorted(names) if not hasattr(S, n)] == []
+    assert hasattr(S, "lv_params_from_yaml") and hasattr(S, "lv_default_params")
+    L = C.CDLL(lv.LIB_PATH)
+    assert not hasattr(L, "lv_synth_world_create")
+    import subprocess
+    needed = subprocess.run(["readelf", "-d", lv.SYNTH_LIB_PATH], capture_output=True, text=True).stdout
+    assert "cudart" not in needed and "libcuda" not in needed
+
+
 def test_struct_layouts_match_the_header(lv):
     assert C.sizeof(lv.IterLog) == 8 + 4 + 4 + 8 * (144 + 12 + 23 + 26)
     p = lv.default_params()
