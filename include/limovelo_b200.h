@@ -76,9 +76,11 @@ typedef struct lv_params {
     float I_Rotation_L[9];            /* row-major YAML list                               */
     float map_downsample_size;        /* ikd-Tree box_length, Mapper.cpp:65 = 0.2          */
     /* ---- device tuning (not in the reference) ---- */
-    float voxel_size;                 /* edge of the hashed search voxels [m], default 0.5 */
+    float voxel_size;                 /* edge of the hashed search voxels [m], default 0.4; rounded to a whole number
+                                       * (1..3) of map_downsample_size cells: a voxel is k x k x k downsample cells */
     int32_t device;                   /* CUDA device ordinal                               */
-    int32_t sort_queries;             /* 1: reorder the sweep by voxel key once per update */
+    int32_t sort_queries;             /* 1: bin the sweep by home voxel once per update and search from shared memory
+                                       * (lv_search_staged_kernel); 0: per-query search from global memory       */
     int64_t max_map_points;           /* capacity of the device map                        */
     int64_t max_points;               /* capacity of one sweep                             */
     void* stream;                     /* cudaStream_t to run on; NULL = own stream         */
@@ -105,7 +107,7 @@ typedef struct lv_profile {
     int64_t idle_launches;
     /* measure_ms split by kernel (each launched once per h-evaluation) */
     double search_ms;         /* lv_search_kernel: exact 5-NN at level 0                   */
-    double search_upper_ms;   /* lv_search_upper_kernel: the queries level 0 cannot certify */
+    double search_upper_ms;   /* lv_search_rings_kernel: the queries level 0 cannot certify */
     double fit_ms;            /* lv_fit_kernel: plane fit, Jacobian rows, normal equations  */
     double reuse_ms;          /* lv_reuse_kernel: neighbours carried over from the previous evaluation */
 } lv_profile;
@@ -130,11 +132,20 @@ lv_status lv_map_build(lv_handle h, const float* xyz, int64_t m);
 /* Mapper::add on an existing map == KD_TREE::Add_Points (Mapper.cpp:73-76,
  * ikd_Tree.cpp:478-573): 0.2 m voxel rule when downsample != 0.                              */
 lv_status lv_map_add(lv_handle h, const float* xyz, int64_t n, int downsample);
-int64_t lv_map_size(lv_handle h);                             /* Mapper::size  (Mapper.cpp:32) */
+/* Both are ASYNCHRONOUS on the handle's stream (no host round trip: every count lives on the device; the host
+ * buffer may be reused when the call returns only if it is pinned — pageable memory is staged by the runtime).
+ * Running out of table / arena space is flagged on the device and reported as LV_ERR_CAPACITY by the next call
+ * that synchronises anyway (lv_map_size, lv_map_status, lv_correct, lv_last_logs).                              */
+int64_t lv_map_size(lv_handle h);                             /* Mapper::size  (Mapper.cpp:32); synchronises */
 int lv_map_exists(lv_handle h);                               /* Mapper::exists (Mapper.cpp:36) */
-int64_t lv_map_points(lv_handle h, float* xyz_out, int64_t cap); /* KD_TREE::flatten            */
-/* same as lv_map_build but xyz is a DEVICE pointer (data already resident in HBM)            */
+lv_status lv_map_status(lv_handle h);                         /* synchronises; LV_OK or LV_ERR_CAPACITY       */
+/* KD_TREE::flatten: the map's points in insertion order; returns their number; synchronises  */
+int64_t lv_map_points(lv_handle h, float* xyz_out, int64_t cap);
+/* same as lv_map_build / lv_map_add but xyz is a DEVICE pointer (data already resident in HBM, e.g. the deskewed
+ * sweep transformed by the update's own result): correct -> add never leaves the GPU.  The buffer must stay valid
+ * until the stream has passed the call.                                                                        */
 lv_status lv_map_build_device(lv_handle h, const float* d_xyz, int64_t m);
+lv_status lv_map_add_device(lv_handle h, const float* d_xyz, int64_t n, int downsample);
 
 /* ---- operator boundary: the measurement model IKFoM calls (esekfom.hpp:128,1637) --------- */
 /* compat mode: fills h_x (Nm x 12, COLUMN-major like Eigen::MatrixXd) and h (Nm) exactly as

@@ -91,6 +91,8 @@ def lib():
     L.lv_map_points.argtypes = [vp, fp, i64]
     L.lv_map_points.restype = i64
     L.lv_map_build_device.argtypes = [vp, vp, i64]
+    L.lv_map_add_device.argtypes = [vp, vp, i64, C.c_int]
+    L.lv_map_status.argtypes = [vp]
     L.lv_measure.argtypes = [vp, dp, fp, i64, dp, dp, C.POINTER(i64)]
     L.lv_measure_reduced.argtypes = [vp, dp, fp, i64, dp, dp, C.POINTER(i64)]
     L.lv_match_all.argtypes = [vp, dp, fp, i64, C.POINTER(C.c_uint8), i32p, fp, fp, fp, fp]
@@ -338,6 +340,14 @@ class Localizer:
     def map_add(self, xyz, downsample=True):
         xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
         return _check(self.L.lv_map_add(self.h, _f(xyz), xyz.shape[0], int(downsample)))
+
+    def map_add_device(self, d_xyz, n, downsample=True):
+        """Mapper::add from a device buffer; asynchronous (no host round trip)"""
+        return _check(self.L.lv_map_add_device(self.h, C.c_void_p(d_xyz), int(n), int(downsample)))
+
+    def map_status(self):
+        """synchronises; raises on LV_ERR_CAPACITY (device map out of table / arena space)"""
+        return _check(self.L.lv_map_status(self.h))
 
     def map_size(self):
         return int(self.L.lv_map_size(self.h))

@@ -174,7 +174,6 @@ static MeasureArgs make_measure_args(lv_context* h, const float* d_xyz, int64_t 
     float f = (float)a.gate_d2;
     if ((double)f < a.gate_d2) f = nextafterf(f, INFINITY);
     a.max_d2 = f;
-    a.max_ring = 1;
     a.planes_threshold = h->prm.PLANES_THRESHOLD;
     a.estimate_extrinsics = h->prm.estimate_extrinsics;
     a.partials = h->d_partials;
@@ -198,13 +197,38 @@ const char* lv_last_error(void) { return g_last_error.c_str(); }
 const char* lv_version(void) { return "limovelo_b200 0.1 (sm_100a)"; }
 int64_t lv_result_bytes(void) { return (int64_t)sizeof(UpdateCtrl); }
 
+/* every failure after `new lv_context` goes through here: nothing of a half-built context survives */
+#define LV_CREATE_CUDA(call)                                                                     \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            char buf__[512];                                                                     \
+            snprintf(buf__, sizeof(buf__), "%s:%d: %s -> %s", __FILE__, __LINE__, #call,         \
+                     cudaGetErrorString(e__));                                                   \
+            lv_destroy(h);                                                                       \
+            set_error(buf__);                                                                    \
+            return LV_ERR_CUDA;                                                                  \
+        }                                                                                        \
+    } while (0)
+
 lv_status lv_create(const lv_params* p, lv_handle* out) {
     if (!p || !out) return LV_ERR_ARG;
     *out = nullptr;
+    /* all argument checks come before the first allocation */
     if (p->NUM_MATCH_POINTS != 5) { set_error("NUM_MATCH_POINTS must be 5 (5x3 plane fit)"); return LV_ERR_ARG; }
-    if (p->MAX_NUM_ITERS < 0 || p->MAX_NUM_ITERS + 1 > LV_MAX_EVALS)   /* 0: a single h-evaluation (esekfom.hpp:1634 runs i = -1 .. max-1) */ { set_error("MAX_NUM_ITERS out of range"); return LV_ERR_ARG; }
-    if (!(p->voxel_size > 0.f) || p->max_map_points <= 0 || p->max_points <= 0) { set_error("bad capacity / voxel_size"); return LV_ERR_ARG; }
-    if (p->max_map_points > 0x7FFFFFF0ll || p->max_points > 0x7FFFFFF0ll) { set_error("capacity beyond 2^31 points"); return LV_ERR_ARG; }
+    if (p->MAX_NUM_ITERS < 0 || p->MAX_NUM_ITERS + 1 > LV_MAX_EVALS) {   /* 0: a single h-evaluation (esekfom.hpp:1634 runs i = -1 .. max-1) */
+        set_error("MAX_NUM_ITERS out of range");
+        return LV_ERR_ARG;
+    }
+    if (!(p->voxel_size > 0.f) || !(p->map_downsample_size > 0.f) || p->max_map_points <= 0 || p->max_points <= 0) {
+        set_error("bad capacity / voxel_size / map_downsample_size");
+        return LV_ERR_ARG;
+    }
+    if (p->max_map_points > (1ll << 24) || p->max_points > (1ll << 24)) { set_error("capacity beyond 2^24 points"); return LV_ERR_ARG; }
+    if (!(p->MAX_DIST_PLANE > 0.0) || p->MAX_DIST_PLANE > 48.0 * (double)p->map_downsample_size) {
+        set_error("MAX_DIST_PLANE must be positive and at most 48 map_downsample_size (ring search bound)");
+        return LV_ERR_ARG;
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
         set_error("no CUDA device available (there is no CPU fallback)");
@@ -215,50 +239,30 @@ lv_status lv_create(const lv_params* p, lv_handle* out) {
     h->prm = *p;
     memset(&h->prof, 0, sizeof(h->prof));
     memset(h->logs, 0, sizeof(h->logs));
+    memset(&h->map, 0, sizeof(h->map));
     fill_iprm(h);
     if (p->stream) { h->stream = (cudaStream_t)p->stream; h->own_stream = false; }
-    else { LV_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
-    MapBuffers& m = h->map;
-    memset(&m, 0, sizeof(m));
-    m.cap = p->max_map_points;
-    m.cell = p->voxel_size;
-    m.inv_cell = 1.0f / p->voxel_size;
-    m.sort_tmp_bytes = map_sort_tmp_bytes(m.cap);
-    { const size_t t2 = lvh_map_add_tmp_bytes(m.cap); if (t2 > m.sort_tmp_bytes) m.sort_tmp_bytes = t2; }
-    LV_CUDA(cudaMalloc(&m.xyz, sizeof(float) * 3 * m.cap));
-    LV_CUDA(cudaMalloc(&m.xyz_alt, sizeof(float) * 3 * m.cap));
-    LV_CUDA(cudaMalloc(&m.keys, sizeof(uint64_t) * m.cap));
-    LV_CUDA(cudaMalloc(&m.keys_sorted, sizeof(uint64_t) * m.cap));
-    LV_CUDA(cudaMalloc(&m.vals, sizeof(uint32_t) * m.cap));
-    LV_CUDA(cudaMalloc(&m.vals_sorted, sizeof(uint32_t) * m.cap));
-    LV_CUDA(cudaMalloc(&m.pts, sizeof(float4) * m.cap));
-    /* pyramid: edge doubles per level until it covers the search radius MAX_DIST_PLANE */
-    m.n_levels = 1;
-    while (m.n_levels < kMaxLevels && (double)m.cell * (double)(1 << (m.n_levels - 1)) < p->MAX_DIST_PLANE) m.n_levels++;
-    if ((double)m.cell * (double)(1 << (m.n_levels - 1)) < p->MAX_DIST_PLANE) {
-        set_error("voxel_size too small: voxel_size * 8 must reach MAX_DIST_PLANE");
-        return LV_ERR_ARG;
-    }
-    LV_CUDA(cudaMalloc(&m.counter, sizeof(uint32_t) * 8));
-    LV_CUDA(cudaMalloc(&m.sort_tmp, m.sort_tmp_bytes));
-    LV_CUDA(cudaMalloc(&h->d_sweep, sizeof(float) * 3 * p->max_points));
-    LV_CUDA(cudaMalloc(&h->d_nn_a, sizeof(int4) * p->max_points));
-    LV_CUDA(cudaMalloc(&h->d_nn_b, sizeof(int2) * p->max_points));
-    LV_CUDA(cudaMalloc(&h->d_hard_list, sizeof(uint32_t) * ((size_t)kHardBuckets * hard_segment(p->max_points) + kCounters)));
-    LV_CUDA(cudaMalloc(&h->d_ref, sizeof(float4) * p->max_points));
-    LV_CUDA(cudaMalloc(&h->d_redo, sizeof(uint32_t) * (p->max_points + 64)));   /* + one block of slack: read speculatively */
+    else { LV_CREATE_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true; }
+    LV_CREATE_CUDA(map_alloc(h->map, p->max_map_points, p->max_points, p->voxel_size, p->map_downsample_size));
+    { int l = 0; LV_CREATE_CUDA(map_clear(h->map, h->stream, &l)); }
+    LV_CREATE_CUDA(cudaMalloc(&h->d_sweep, sizeof(float) * 3 * p->max_points));
+    LV_CREATE_CUDA(cudaMalloc(&h->d_nn_a, sizeof(int4) * p->max_points));
+    LV_CREATE_CUDA(cudaMalloc(&h->d_nn_b, sizeof(int2) * p->max_points));
+    LV_CREATE_CUDA(cudaMalloc(&h->d_hard_list, sizeof(uint32_t) * ((size_t)kHardBuckets * hard_segment(p->max_points) + kCounters)));
+    LV_CREATE_CUDA(cudaMalloc(&h->d_ref, sizeof(float4) * p->max_points));
+    LV_CREATE_CUDA(cudaMalloc(&h->d_redo, sizeof(uint32_t) * (p->max_points + 64)));   /* + one block of slack: read speculatively */
     h->use_reuse = getenv("LV_NO_REUSE") == nullptr;
     h->use_pdl = getenv("LV_NO_PDL") == nullptr;
-    LV_CUDA(cudaMalloc(&h->d_job, sizeof(MeasureJob)));
+    LV_CREATE_CUDA(cudaMalloc(&h->d_job, sizeof(MeasureJob)));
     measure_init();
     h->use_graph = getenv("LV_NO_GRAPH") == nullptr;
-    LV_CUDA(cudaMalloc(&h->d_ctrl, sizeof(UpdateCtrl)));
-    LV_CUDA(cudaMemset(h->d_ctrl, 0, sizeof(UpdateCtrl)));
-    LV_CUDA(cudaMallocHost(&h->h_ctrl, sizeof(UpdateCtrl)));
-    LV_CUDA(cudaMalloc(&h->d_partials, sizeof(double) * kPartialStride * (148 * 4 + 8)));
-    LV_CUDA(cudaMalloc(&h->d_reduced, sizeof(double) * 160));
-    LV_CUDA(cudaMallocHost(&h->h_reduced, sizeof(double) * 160));
-    LV_CUDA(cudaMallocHost(&h->h_nevals, sizeof(int32_t) * kNevalsRing));
+    LV_CREATE_CUDA(cudaMalloc(&h->d_ctrl, sizeof(UpdateCtrl)));
+    LV_CREATE_CUDA(cudaMemset(h->d_ctrl, 0, sizeof(UpdateCtrl)));
+    LV_CREATE_CUDA(cudaMallocHost(&h->h_ctrl, sizeof(UpdateCtrl)));
+    LV_CREATE_CUDA(cudaMalloc(&h->d_partials, sizeof(double) * kPartialStride * (148 * 4 + 8)));
+    LV_CREATE_CUDA(cudaMalloc(&h->d_reduced, sizeof(double) * 160));
+    LV_CREATE_CUDA(cudaMallocHost(&h->h_reduced, sizeof(double) * 160));
+    LV_CREATE_CUDA(cudaMallocHost(&h->h_nevals, sizeof(int32_t) * kNevalsRing));
     /* default filter state: identity pose, P = I (esekf constructor); callers normally follow
      * with lv_init_state or lv_set_state */
     for (int i = 0; i < LV_STATE_LEN; ++i) h->x[i] = 0;
@@ -271,36 +275,53 @@ lv_status lv_create(const lv_params* p, lv_handle* out) {
 void lv_destroy(lv_handle h) {
     if (!h) return;
     cudaSetDevice(h->prm.device);
-    cudaStreamSynchronize(h->stream);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     for (auto& e : h->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : h->pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& u : h->graphs) { cudaGraphExecDestroy(u.exec); cudaGraphDestroy(u.graph); }
     cudaFree(h->d_job); cudaFree(h->d_ref); cudaFree(h->d_redo);
     cudaFree(h->d_path); cudaFreeHost(h->h_path); cudaFree(h->d_times); cudaFree(h->d_deskew_in); cudaFree(h->d_bad); cudaFreeHost(h->h_bad);
     ds_free(h->ds); cudaFree(h->d_ds_in); cudaFree(h->d_ds_out);
-    MapBuffers& m = h->map;
-    cudaFree(m.xyz); cudaFree(m.xyz_alt); cudaFree(m.keys); cudaFree(m.keys_sorted); cudaFree(m.vals); cudaFree(m.vals_sorted);
-    cudaFree(m.pts);
-    for (int l = 0; l < kMaxLevels; ++l) cudaFree(m.level[l].table);
-    cudaFree(m.halo); cudaFree(m.bsize); cudaFree(m.bstart);
-    cudaFree(m.counter); cudaFree(m.sort_tmp);
+    map_free(h->map);
     cudaFree(h->d_sweep); cudaFree(h->d_nn_a); cudaFree(h->d_nn_b); cudaFree(h->d_hard_list); cudaFree(h->d_ctrl); cudaFreeHost(h->h_ctrl); cudaFree(h->d_partials);
     cudaFree(h->d_reduced); cudaFreeHost(h->h_reduced); cudaFreeHost(h->h_nevals); cudaFree(h->d_flush);
     cudaFree(h->d_valid); cudaFree(h->d_nn_idx); cudaFree(h->d_nn_sqd); cudaFree(h->d_plane);
     cudaFree(h->d_dist); cudaFree(h->d_gworld); cudaFree(h->d_rows);
-    if (h->own_stream) cudaStreamDestroy(h->stream);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
 
 /* ---- Mapper ---------------------------------------------------------------------------------- */
-static lv_status rebuild(lv_context* h) {
+/* device-side error flags of the map (table / arena exhausted) -> status.  Call after a stream synchronisation that
+ * followed map_fetch_counters(). */
+static lv_status map_status_from_mirror(lv_context* h) {
+    const uint32_t err = h->map.h_counters[kCtrError];
+    if (!err) return LV_OK;
+    char buf[256];
+    snprintf(buf, sizeof(buf), "device map out of capacity (flags 0x%x: 1 voxel table, 2 arena, 4 extent too large, 8 list, 16 block table): raise max_map_points",
+             err);
+    set_error(buf);
+    return LV_ERR_CAPACITY;
+}
+static void count_map_launches(lv_context* h, int launches) { h->prof.total_launches += launches; }
+
+static lv_status map_build_device_impl(lv_context* h, const float* d_xyz, int64_t m) {
     EventPair ep;
     const bool pr = prof_begin(h, 2, &ep);
     int launches = 0;
-    LV_CUDA(map_rebuild(h->map, h->stream, &launches));
-    h->map_version++;
+    LV_CUDA(map_clear(h->map, h->stream, &launches));
+    LV_CUDA(map_add(h->map, d_xyz, m, 0, h->stream, &launches));              /* Build: no downsampling (Mapper.cpp:68-71) */
     if (pr) prof_end(h, &ep);
-    h->prof.total_launches += launches;
+    count_map_launches(h, launches);
+    return LV_OK;
+}
+static lv_status map_add_device_impl(lv_context* h, const float* d_xyz, int64_t n, int downsample) {
+    EventPair ep;
+    const bool pr = prof_begin(h, 2, &ep);
+    int launches = 0;
+    LV_CUDA(map_add(h->map, d_xyz, n, downsample ? 1 : 0, h->stream, &launches));
+    if (pr) prof_end(h, &ep);
+    count_map_launches(h, launches);
     return LV_OK;
 }
 
@@ -309,42 +330,55 @@ lv_status lv_map_build(lv_handle h, const float* xyz, int64_t m) {
     if (m <= 0) return LV_OK;                                    /* Mapper.cpp:23 */
     if (m > h->map.cap) { set_error("map capacity exceeded"); return LV_ERR_CAPACITY; }
     LV_CUDA(cudaSetDevice(h->prm.device));
-    LV_CUDA(cudaMemcpyAsync(h->map.xyz, xyz, sizeof(float) * 3 * m, cudaMemcpyHostToDevice, h->stream));
-    h->map.n = m;
-    return rebuild(h);
+    LV_CUDA(cudaMemcpyAsync(h->map.stage_xyz, xyz, sizeof(float) * 3 * m, cudaMemcpyHostToDevice, h->stream));
+    return map_build_device_impl(h, h->map.stage_xyz, m);
 }
 lv_status lv_map_build_device(lv_handle h, const float* d_xyz, int64_t m) {
     if (!h || (!d_xyz && m > 0)) return LV_ERR_ARG;
     if (m <= 0) return LV_OK;
     if (m > h->map.cap) { set_error("map capacity exceeded"); return LV_ERR_CAPACITY; }
     LV_CUDA(cudaSetDevice(h->prm.device));
-    LV_CUDA(cudaMemcpyAsync(h->map.xyz, d_xyz, sizeof(float) * 3 * m, cudaMemcpyDeviceToDevice, h->stream));
-    h->map.n = m;
-    return rebuild(h);
+    return map_build_device_impl(h, d_xyz, m);
 }
-int64_t lv_map_size(lv_handle h) { return h ? h->map.n : 0; }
-int lv_map_exists(lv_handle h) { return (h && h->map.n > 0) ? 1 : 0; }
+int64_t lv_map_size(lv_handle h) {
+    if (!h || h->map.empty) return 0;
+    if (cudaSetDevice(h->prm.device) != cudaSuccess) return -1;
+    if (map_fetch_counters(h->map, h->stream) != cudaSuccess || cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
+    map_status_from_mirror(h);
+    return (int64_t)(int32_t)h->map.h_counters[kCtrPoints];
+}
+int lv_map_exists(lv_handle h) { return (h && !h->map.empty) ? 1 : 0; }
+lv_status lv_map_status(lv_handle h) {
+    if (!h) return LV_ERR_ARG;
+    LV_CUDA(cudaSetDevice(h->prm.device));
+    LV_CUDA(map_fetch_counters(h->map, h->stream));
+    LV_CUDA(cudaStreamSynchronize(h->stream));
+    return map_status_from_mirror(h);
+}
 int64_t lv_map_points(lv_handle h, float* out, int64_t cap) {
-    if (!h) return 0;
-    const int64_t n = h->map.n < cap ? h->map.n : cap;
-    if (n > 0 && out) {
-        cudaSetDevice(h->prm.device);
-        if (cudaMemcpyAsync(out, h->map.xyz, sizeof(float) * 3 * n, cudaMemcpyDeviceToHost, h->stream) != cudaSuccess) return -1;
-        if (cudaStreamSynchronize(h->stream) != cudaSuccess) return -1;
-    }
-    return h->map.n;
+    if (!h || h->map.empty) return 0;
+    if (cudaSetDevice(h->prm.device) != cudaSuccess) return -1;
+    int64_t n = 0;
+    if (map_points_sorted(h->map, out, cap, &n, h->stream) != cudaSuccess) return -1;
+    return n;
 }
 
 lv_status lv_map_add(lv_handle h, const float* xyz, int64_t n, int downsample) {
     if (!h || (!xyz && n > 0)) return LV_ERR_ARG;
     if (n <= 0) return LV_OK;                                    /* Mapper.cpp:23 */
-    if (h->map.n == 0) return lv_map_build(h, xyz, n);           /* Mapper.cpp:26 */
+    if (h->map.empty) return lv_map_build(h, xyz, n);            /* Mapper.cpp:26 */
+    if (n > h->map.add_cap) { set_error("more points than one lv_map_add can take (max_map_points)"); return LV_ERR_CAPACITY; }
     LV_CUDA(cudaSetDevice(h->prm.device));
-    int launches = 0;
-    const lv_status st = (lv_status)lvh_map_add_points(h->map, xyz, n, downsample, h->prm.map_downsample_size, h->stream, &launches);
-    if (st != LV_OK) { set_error("lv_map_add failed (capacity or CUDA error)"); return st; }
-    h->prof.total_launches += launches;
-    return rebuild(h);
+    LV_CUDA(cudaMemcpyAsync(h->map.stage_xyz, xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
+    return map_add_device_impl(h, h->map.stage_xyz, n, downsample);
+}
+lv_status lv_map_add_device(lv_handle h, const float* d_xyz, int64_t n, int downsample) {
+    if (!h || (!d_xyz && n > 0)) return LV_ERR_ARG;
+    if (n <= 0) return LV_OK;
+    if (n > h->map.add_cap) { set_error("more points than one lv_map_add can take (max_map_points)"); return LV_ERR_CAPACITY; }
+    LV_CUDA(cudaSetDevice(h->prm.device));
+    if (h->map.empty) return map_build_device_impl(h, d_xyz, n);
+    return map_add_device_impl(h, d_xyz, n, downsample);
 }
 
 /* ---- state ----------------------------------------------------------------------------------- */
@@ -548,6 +582,7 @@ static lv_status enqueue_update_kernels(lv_context* h, const float* d_xyz, int64
 
 static lv_status fetch_results(lv_context* h) {
     LV_CUDA(cudaMemcpyAsync(h->h_ctrl, h->d_ctrl, sizeof(UpdateCtrl), cudaMemcpyDeviceToHost, h->stream));
+    LV_CUDA(map_fetch_counters(h->map, h->stream));       /* 64 bytes: the map's error flags ride along */
     LV_CUDA(cudaStreamSynchronize(h->stream));
     const UpdateCtrl* c = h->h_ctrl;
     memcpy(h->x, c->x, sizeof(h->x));
@@ -557,6 +592,7 @@ static lv_status fetch_results(lv_context* h) {
     h->last_status = c->status;
     h->state_dirty = false;
     h->pending_fetch = false;
+    if (c->status == LV_OK && map_status_from_mirror(h) != LV_OK) return LV_ERR_CAPACITY;
     return (lv_status)c->status;
 }
 
@@ -564,7 +600,7 @@ lv_status lv_correct(lv_handle h, const float* xyz, int64_t n, double time, lv_i
                      double* x_out, double* P_out) {
     if (!h || !xyz || n <= 0) return LV_ERR_ARG;
     if (n_evals) *n_evals = 0;
-    if (h->map.n == 0) return LV_EMPTY_MAP;                       /* Localizator.cpp:24 */
+    if (h->map.empty) return LV_EMPTY_MAP;                       /* Localizator.cpp:24 */
     if (n > h->prm.max_points) { set_error("sweep capacity exceeded"); return LV_ERR_CAPACITY; }
     LV_CUDA(cudaSetDevice(h->prm.device));
     LV_CUDA(cudaMemcpyAsync(h->d_sweep, xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
@@ -581,7 +617,7 @@ lv_status lv_correct(lv_handle h, const float* xyz, int64_t n, double time, lv_i
 
 lv_status lv_correct_device(lv_handle h, const float* d_xyz, int64_t n, double time) {
     if (!h || !d_xyz || n <= 0) return LV_ERR_ARG;
-    if (h->map.n == 0) return LV_EMPTY_MAP;
+    if (h->map.empty) return LV_EMPTY_MAP;
     LV_CUDA(cudaSetDevice(h->prm.device));
     lv_status s = enqueue_update(h, d_xyz, n);
     h->last_time_updated = time;
@@ -653,7 +689,7 @@ lv_status lv_measure_reduced(lv_handle h, const double* x, const float* xyz, int
                              int64_t* nm) {
     if (!h || !x || !xyz || n <= 0) return LV_ERR_ARG;
     if (nm) *nm = 0;
-    if (h->map.n == 0) return LV_EMPTY_MAP;
+    if (h->map.empty) return LV_EMPTY_MAP;
 #ifdef LV_PHASE_TRACE
     lv_debug_phases(nullptr, 1);
 #endif
@@ -692,7 +728,7 @@ lv_status lv_measure_reduced(lv_handle h, const double* x, const float* xyz, int
 lv_status lv_measure(lv_handle h, const double* x, const float* xyz, int64_t n, double* h_x, double* h_vec, int64_t* nm) {
     if (!h || !x || !xyz || n <= 0 || !nm) return LV_ERR_ARG;
     *nm = 0;
-    if (h->map.n == 0) return LV_EMPTY_MAP;
+    if (h->map.empty) return LV_EMPTY_MAP;
     lv_status s = run_measure_once(h, x, xyz, n, true, false);
     if (s != LV_OK) return s;
     std::vector<double> rows(13 * (size_t)n);
@@ -719,7 +755,7 @@ lv_status lv_measure(lv_handle h, const double* x, const float* xyz, int64_t n, 
 lv_status lv_match_all(lv_handle h, const double* x, const float* xyz, int64_t n, uint8_t* valid, int32_t* nn_idx,
                        float* nn_sqd, float* plane, float* dist, float* g_world) {
     if (!h || !x || !xyz || n <= 0) return LV_ERR_ARG;
-    if (h->map.n == 0) return LV_EMPTY_MAP;
+    if (h->map.empty) return LV_EMPTY_MAP;
     lv_status s = run_measure_once(h, x, xyz, n, false, true);
     if (s != LV_OK) return s;
     if (valid) LV_CUDA(cudaMemcpyAsync(valid, h->d_valid, (size_t)n, cudaMemcpyDeviceToHost, h->stream));

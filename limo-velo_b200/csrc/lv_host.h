@@ -11,15 +11,9 @@
 
 #include "../../include/limovelo_b200.h"
 
-namespace lv { struct MapBuffers; }
-
 /* Localizator::init_IKFoM_state (src/Modules/Localizator.cpp:135-153) */
 void lvh_init_state(const lv_params& prm, const float q_imu[4], double* x, double* P);
 /* Localizator::propagate -> esekf::predict (Localizator.cpp:159-173, esekfom.hpp:279-384) */
 void lvh_predict(const lv_params& prm, const double acc[3], const double gyro[3], double dt, double* x, double* P);
-/* KD_TREE::Add_Points on the device map (lv_map_add.cu); returns lv_status */
-int lvh_map_add_points(lv::MapBuffers& b, const float* xyz_host, int64_t n, int downsample, float ds, cudaStream_t st,
-                       int* launches);
-size_t lvh_map_add_tmp_bytes(int64_t cap);
 
 #endif

@@ -39,7 +39,6 @@ struct MeasureArgs {
     UpdateCtrl* prep;          /* non-NULL: block 0 of the fit kernel runs ieskf_prepare() */
     float max_d2;              /* smallest float >= MAX_DIST_PLANE^2 (search radius^2)    */
     double gate_d2;            /* MAX_DIST_PLANE^2 in double (Plane.cpp:42)               */
-    int32_t max_ring;
     float planes_threshold;
     int32_t estimate_extrinsics;
     double* partials;          /* [grid][kPartialStride]: 78 + 12 sums, count             */
@@ -61,40 +60,39 @@ struct MeasureArgs {
     uint32_t* redo_list;       /* n: queries whose neighbours could not be reused (Kv -> K1)  */
 };
 
-/* one level of the voxel pyramid */
-struct MapLevel {
-    uint4* table;              /* hash slots (2 x uint4 each), grown on demand             */
-    uint64_t table_cap;        /* allocated uint4 elements                                 */
-    uint32_t mask;             /* slots in use - 1                                         */
-};
-
-/* device map storage + scratch for the per-sweep rebuild */
+/* device map storage (layout: lv_voxel_map.h) + scratch of one add */
 struct MapBuffers {
-    float* xyz;                /* map points, insertion order (flatten order), cap x 3     */
-    float* xyz_alt;            /* second buffer: lv_map_add compacts into it, then swaps    */
-    int64_t n, cap;
-    uint64_t* keys;            /* cap */
-    uint64_t* keys_sorted;     /* cap */
-    uint32_t* vals;
-    uint32_t* vals_sorted;
-    float4* pts;               /* cap, Morton-sorted                                       */
-    MapLevel level[kMaxLevels];
-    int32_t n_levels;
-    float4* halo;              /* level-0 halo buckets, grown on demand                    */
-    uint64_t halo_cap, halo_n;
-    uint32_t* bsize;           /* per level-0 slot: halo bucket size / offset              */
-    uint32_t* bstart;
-    uint64_t bs_cap, bs_cap2;
-    uint32_t* counter;         /* device scalars                                           */
+    MapGrid grid;
+    uint4* table;              /* voxel slots (2 x uint4 each)                               */
+    uint32_t slots;
+    uint4* btable;             /* block slots                                                 */
+    uint32_t bslots;
+    float4* arena;             /* own extents + halo buckets                                  */
+    uint32_t arena_cap;
+    uint32_t* counters;        /* kMapCounters device words                                   */
+    uint32_t* h_counters;      /* pinned mirror (map_fetch_counters)                          */
+    uint32_t* touched;
+    uint32_t* dirty;
+    uint32_t list_cap;
+    float* stage_xyz;          /* device copy of host points handed to lv_map_build / lv_map_add: add_cap x 3 */
+    uint32_t *skeys, *skeys_alt, *svals, *svals_alt;   /* sort of the new points (add_cap each) */
     void* sort_tmp;
     size_t sort_tmp_bytes;
-    float cell, inv_cell;      /* finest level                                             */
+    int sort_bits;
+    int64_t cap;               /* max_map_points (sizes the tables and the arena)             */
+    int64_t add_cap;           /* most points one build / add can take                        */
+    int64_t n_inserted;        /* ids handed out so far                                       */
+    bool empty;                /* nothing was ever added (Mapper::exists, Mapper.cpp:32-34)   */
 };
 
-size_t map_sort_tmp_bytes(int64_t cap);
-/* K0: rebuild the hashed-voxel structure from b.xyz[0..n).  Returns launches issued; synchronises
- * the stream once (to size the hash table).                                                    */
-cudaError_t map_rebuild(MapBuffers& b, cudaStream_t st, int* launches);
+cudaError_t map_alloc(MapBuffers& b, int64_t max_map_points, int64_t max_points, float voxel_size, float ds);
+void map_free(MapBuffers& b);
+/* empty the map (table, block table, counters); asynchronous */
+cudaError_t map_clear(MapBuffers& b, cudaStream_t st, int* launches);
+/* KD_TREE::Build (downsample = 0 on an empty map) / Add_Points: n points in DEVICE memory; asynchronous, no host round trip */
+cudaError_t map_add(MapBuffers& b, const float* d_xyz, int64_t n, int downsample, cudaStream_t st, int* launches);
+cudaError_t map_fetch_counters(MapBuffers& b, cudaStream_t st);
+cudaError_t map_points_sorted(MapBuffers& b, float* host_out, int64_t cap, int64_t* n_out, cudaStream_t st);
 VoxelMapView map_view(const MapBuffers& b);
 
 int measure_grid(int n);
@@ -108,7 +106,7 @@ cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st, cons
 cudaError_t launch_ieskf_begin(UpdateCtrl* c, MeasureJob* job, const float* xyz, int n, uint32_t* counters, cudaStream_t st);
 const void* ieskf_begin_kernel_ptr();
 void measure_init();                          /* constant tables; call once before any capture           */
-/* the three kernels of launch_measure() (search instance, search-upper, fit) with their launch shapes, for
+/* the three kernels of launch_measure() (search instance, search-rings, fit) with their launch shapes, for
  * patching the nodes of a captured update when the map view changes */
 struct MeasureKernelShape { const void* func; unsigned grid, block; };
 enum { kMeasureKernels = 5 };   /* search, search-upper, fit, search over the redo list, reuse */

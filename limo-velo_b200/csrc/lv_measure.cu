@@ -12,8 +12,8 @@
  * and the 23x23 algebra between two evaluations (esekfom.hpp:1647-1817, csrc/lv_ieskf.h).
  *
  * Kernels of one evaluation: lv_reuse_kernel (evaluations after the first: keep the neighbours the
- * exact search provably returns again), lv_search_kernel (exact 5-NN at level 0, thin, 4 lanes per query),
- * lv_search_upper_kernel (the queries level 0 cannot certify, one warp each), lv_fit_kernel (plane fit, Jacobian
+ * exact search provably returns again), lv_search_kernel (exact 5-NN at level 0, thin, 8 lanes per query),
+ * lv_search_rings_kernel (the queries level 0 cannot certify, one warp each), lv_fit_kernel (plane fit, Jacobian
  * row, the 78 + 12 unique normal-equation sums per block in a fixed order; one spare block runs ieskf_prepare),
  * lv_ieskf_step_kernel (one block: reduction of the partials, gain, dx, next frame, loop control).  H (Nm x 12
  * fp64) is never materialised.  Inside an update every kernel is launched with programmatic dependent launch and
@@ -45,10 +45,6 @@ __device__ unsigned g_lv_phase[3][16384];
 #define LV_PHASE(k, v) do { if ((threadIdx.x & 31) == 0) { const unsigned w_ = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; if (w_ < 16384u) g_lv_phase[k][w_] = (v); } } while (0)
 #else
 #define LV_PHASE(k, v)
-#endif
-#ifdef LV_WATCHDOG
-#define LV_WATCHDOG_TU
-__device__ unsigned long long g_lv_wd[8];
 #endif
 #include "lv_internal.h"
 
@@ -111,18 +107,11 @@ __device__ __forceinline__ JobView job_view(const MeasureArgs& a) {
 
 #define LV_ROW_STRIDE (kMeasureThreads + 1)   /* +1 double: 13 row-columns land in distinct banks */
 #define LV_SEARCH_THREADS 128
-#define LV_GROUP 4                              /* lanes per query in K1 (LV_SEARCH_GROUP=1|2|4|8 overrides) */
+#define LV_GROUP 8                              /* lanes per query in K1 (LV_SEARCH_GROUP=1|8 overrides) */
 
-__device__ __forceinline__ void store_neighbours(const MeasureArgs& a, int qi, const Top5& t, bool in_pts) {
-    int4 o;
-    int i4 = t.i4;
-    o.x = t.i0; o.y = t.i1; o.z = t.i2; o.w = t.i3;
-    if (in_pts) {   /* positions p in pts[] are stored as -2 - p, positions in halo[] as they are, -1 = none */
-        o.x = o.x < 0 ? -1 : -2 - o.x; o.y = o.y < 0 ? -1 : -2 - o.y; o.z = o.z < 0 ? -1 : -2 - o.z;
-        o.w = o.w < 0 ? -1 : -2 - o.w; i4 = i4 < 0 ? -1 : -2 - i4;
-    }
-    a.nn_a[qi] = o;
-    a.nn_b[qi] = make_int2(i4, __float_as_int(t.d4));
+__device__ __forceinline__ void store_neighbours(const MeasureArgs& a, int qi, const Top5& t) {
+    a.nn_a[qi] = make_int4(t.i0, t.i1, t.i2, t.i3);                  /* positions in the arena, -1 = none */
+    a.nn_b[qi] = make_int2(t.i4, __float_as_int(t.d4));
 }
 /* what a later evaluation needs to reuse this answer (lb <= 0: do not) */
 __device__ __forceinline__ void store_ref(const MeasureArgs& a, int qi, const float* g, float lb) {
@@ -172,7 +161,7 @@ __global__ void __launch_bounds__(LV_SEARCH_THREADS) lv_search_kernel(const Meas
     if (have) {
         rt_apply(T, jb.xyz[3 * qi], jb.xyz[3 * qi + 1], jb.xyz[3 * qi + 2], g);   /* Mapper.cpp:51 */
         const bool finite = (fabsf(g[0]) < 1e9f) && (fabsf(g[1]) < 1e9f) && (fabsf(g[2]) < 1e9f);
-        if (finite) st = level0_probe(a.map, g[0], g[1], g[2], &bs, &bc) ? 1 : 2;
+        if (finite) st = level0_probe(a.map, g[0], g[1], g[2], &bs, &bc) >= 0 ? 1 : 2;
     }
     Top5 t;
     float region = 0.f;
@@ -180,7 +169,7 @@ __global__ void __launch_bounds__(LV_SEARCH_THREADS) lv_search_kernel(const Meas
     const bool settled = level0_scan<Grp>(a.map, g[0], g[1], g[2], a.max_d2, bs, bc, st == 1, t, &region);
     LV_PHASE(0, 3u);
     if (have && (threadIdx.x & (G - 1)) == 0) {
-        store_neighbours(a, qi, t, false);
+        store_neighbours(a, qi, t);
         const bool hard = st == 2 || (st == 1 && !settled);
         store_ref(a, qi, g, (st == 1 && settled) ? outsider_bound(t.d5, region) : 0.f);
         if (hard) {
@@ -209,22 +198,19 @@ __global__ void __launch_bounds__(128) lv_reuse_kernel(const MeasureArgs a) {
     float p[3] = {0.f, 0.f, 0.f}, q[5][3];
     float ref[4] = {0.f, 0.f, 0.f, 0.f};
     int id[5] = {-1, -1, -1, -1, -1};
-    bool general = false, cand = false;
+    bool cand = false;
     if (have) {
         p[0] = jb.xyz[3 * qi]; p[1] = jb.xyz[3 * qi + 1]; p[2] = jb.xyz[3 * qi + 2];
         const float4 r4 = a.ref[qi];
         const int4 na = a.nn_a[qi];
         const int2 nb = a.nn_b[qi];
         ref[0] = r4.x; ref[1] = r4.y; ref[2] = r4.z; ref[3] = r4.w;
-        cand = r4.w > 0.f && nb.x != -1;
+        cand = r4.w > 0.f && nb.x >= 0;
         if (cand) {
-            general = nb.x < -1;                 /* positions in pts[] (stored as -2 - p) or in halo[] */
-            const float4* src = general ? a.map.pts : a.map.halo;
             id[0] = na.x; id[1] = na.y; id[2] = na.z; id[3] = na.w; id[4] = nb.x;
 #pragma unroll
             for (int k = 0; k < 5; ++k) {
-                id[k] = general ? -2 - id[k] : id[k];
-                const float4 v = load_point(src + id[k]);
+                const float4 v = load_point(a.map.arena + id[k]);
                 q[k][0] = v.x; q[k][1] = v.y; q[k][2] = v.z;
             }
         }
@@ -241,7 +227,7 @@ __global__ void __launch_bounds__(128) lv_reuse_kernel(const MeasureArgs a) {
         redo = true;
         Top5 t;
         if (cand && query_reusable(ref, g, q, id, a.max_d2, t)) {
-            store_neighbours(a, qi, t, general);
+            store_neighbours(a, qi, t);
             redo = false;
         }
     }
@@ -258,10 +244,10 @@ __global__ void __launch_bounds__(128) lv_reuse_kernel(const MeasureArgs a) {
 }
 
 /*
- * K1b — search, upper levels: one WARP per query K1 could not certify (knn5_upper).  The work list
+ * K1b — search beyond ring 1: one WARP per query K1 could not certify (knn5_rings).  The work list
  * length lives on the device; a fixed grid strides over it, so no host round trip is needed.
  */
-__global__ void __launch_bounds__(128) lv_search_upper_kernel(const MeasureArgs a) {
+__global__ void __launch_bounds__(128) lv_search_rings_kernel(const MeasureArgs a) {
     /* flags, frame and job were written two or more kernels ago: safe to fetch while the search still runs
      * (a kernel triggers its successor only after its own wait, so "two kernels ago" is complete by now) */
     LV_TL_SCHED();
@@ -283,9 +269,7 @@ __global__ void __launch_bounds__(128) lv_search_upper_kernel(const MeasureArgs 
     }
     const uint32_t n_hard = __shfl_sync(0xffffffffu, incl, 31);
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    LV_WD_INIT();
     for (uint32_t h = warp; h < n_hard; h += n_warps) {
-        LV_WD(6, n_hard, n_warps)
         int lo = 0;                                     /* first segment whose inclusive prefix exceeds h */
 #pragma unroll
         for (int step = 16; step > 0; step >>= 1) {
@@ -300,9 +284,9 @@ __global__ void __launch_bounds__(128) lv_search_upper_kernel(const MeasureArgs 
         const int2 prev = a.nn_b[qi];   /* level 0's (uncertified) 5th distance bounds the answer from above */
         Top5 u;
         float region = 0.f;
-        knn5_upper<GroupWarp>(a.map, g[0], g[1], g[2], a.max_d2, prev.x >= 0 ? __int_as_float(prev.y) : a.max_d2, u, &region);
+        knn5_rings<GroupWarp>(a.map, g[0], g[1], g[2], a.max_d2, prev.x >= 0 ? __int_as_float(prev.y) : a.max_d2, u, &region);
         if ((threadIdx.x & 31) == 0) {
-            store_neighbours(a, qi, u, true);
+            store_neighbours(a, qi, u);
             store_ref(a, qi, g, outsider_bound(u.d5, region));
         }
     }
@@ -382,13 +366,11 @@ __global__ void __launch_bounds__(kMeasureThreads, 4) lv_fit_kernel(const Measur
             float q[5][3];
             float dsq[5] = {INFINITY, INFINITY, INFINITY, INFINITY, INFINITY};
             int orig[5] = {-1, -1, -1, -1, -1};
-            const bool full = nb.x != -1;
+            const bool full = nb.x >= 0;
             if (full) {
-                const bool general = nb.x < -1;      /* found by the upper-level search: positions in pts[] */
-                const float4* src = general ? a.map.pts : a.map.halo;
-                const float4 q0 = load_point(src + (general ? -2 - na.x : na.x)), q1 = load_point(src + (general ? -2 - na.y : na.y)),
-                             q2 = load_point(src + (general ? -2 - na.z : na.z)), q3 = load_point(src + (general ? -2 - na.w : na.w)),
-                             q4 = load_point(src + (general ? -2 - nb.x : nb.x));
+                const float4* src = a.map.arena;
+                const float4 q0 = load_point(src + na.x), q1 = load_point(src + na.y), q2 = load_point(src + na.z),
+                             q3 = load_point(src + na.w), q4 = load_point(src + nb.x);
                 q[0][0] = q0.x; q[0][1] = q0.y; q[0][2] = q0.z;
                 q[1][0] = q1.x; q[1][1] = q1.y; q[1][2] = q1.z;
                 q[2][0] = q2.x; q[2][1] = q2.y; q[2][2] = q2.z;
@@ -586,7 +568,7 @@ static int search_group() {   /* lanes per query in K1; LV_SEARCH_GROUP override
     if (!group) {
         const char* e = getenv("LV_SEARCH_GROUP");
         group = e ? atoi(e) : LV_GROUP;
-        if (group != 1 && group != 2 && group != 4 && group != 8) group = LV_GROUP;
+        if (group != 1 && group != 8) group = LV_GROUP;
     }
     return group;
 }
@@ -596,14 +578,13 @@ static int search_grid(const MeasureArgs& a, int group) {
 }
 template <bool LIST>
 static const void* search_kernel_ptr(int group) {
-    return group == 1 ? (const void*)lv_search_kernel<1, LIST> : group == 2 ? (const void*)lv_search_kernel<2, LIST>
-         : group == 8 ? (const void*)lv_search_kernel<8, LIST> : (const void*)lv_search_kernel<4, LIST>;
+    return group == 1 ? (const void*)lv_search_kernel<1, LIST> : (const void*)lv_search_kernel<8, LIST>;
 }
 void measure_kernel_shapes(const MeasureArgs& a, int grid, MeasureKernelShape out[kMeasureKernels]) {
     const int group = search_group();
     out[0].func = search_kernel_ptr<false>(group);
     out[0].grid = (unsigned)search_grid(a, group); out[0].block = LV_SEARCH_THREADS;
-    out[1].func = (const void*)lv_search_upper_kernel; out[1].grid = 148 * 2; out[1].block = 128;
+    out[1].func = (const void*)lv_search_rings_kernel; out[1].grid = 148 * 2; out[1].block = 128;
     out[2].func = (const void*)lv_fit_kernel; out[2].grid = (unsigned)(grid + (a.prep ? 1 : 0)); out[2].block = kMeasureThreads;
     out[3].func = search_kernel_ptr<true>(group); out[3].grid = out[0].grid; out[3].block = LV_SEARCH_THREADS;
     out[4].func = (const void*)lv_reuse_kernel; out[4].grid = (unsigned)((a.n + 127) / 128 > 0 ? (a.n + 127) / 128 : 1); out[4].block = 128;
@@ -628,9 +609,7 @@ template <bool LIST>
 static void launch_search(const MeasureArgs& a, int group, int sgrid, cudaStream_t st, bool pdl) {
     switch (group) {
         case 1: launch_k(lv_search_kernel<1, LIST>, sgrid, LV_SEARCH_THREADS, st, pdl, a); break;
-        case 2: launch_k(lv_search_kernel<2, LIST>, sgrid, LV_SEARCH_THREADS, st, pdl, a); break;
-        case 8: launch_k(lv_search_kernel<8, LIST>, sgrid, LV_SEARCH_THREADS, st, pdl, a); break;
-        default: launch_k(lv_search_kernel<4, LIST>, sgrid, LV_SEARCH_THREADS, st, pdl, a); break;
+        default: launch_k(lv_search_kernel<8, LIST>, sgrid, LV_SEARCH_THREADS, st, pdl, a); break;
     }
 }
 
@@ -654,7 +633,7 @@ cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st, cons
     if (dbg_sync) { cudaStreamSynchronize(st); fprintf(stderr, "[lv] search done\n"); fflush(stderr); }
     if (probe) probe->at(probe->ctx, 1);
     static const int upper_grid = getenv("LV_UPPER_GRID") ? atoi(getenv("LV_UPPER_GRID")) : 148 * 2;   /* diagnosis override */
-    launch_k(lv_search_upper_kernel, upper_grid > 0 ? upper_grid : 148 * 2, 128, st, pdl != 0, a);
+    launch_k(lv_search_rings_kernel, upper_grid > 0 ? upper_grid : 148 * 2, 128, st, pdl != 0, a);
     if (dbg_sync) { cudaStreamSynchronize(st); fprintf(stderr, "[lv] search-upper done\n"); fflush(stderr); }
     if (probe) probe->at(probe->ctx, 2);
     launch_k(lv_fit_kernel, grid + (a.prep ? 1 : 0), kMeasureThreads, st, pdl != 0, a);
@@ -700,12 +679,6 @@ extern "C" int lv_debug_phases(unsigned* out /*3 x 16384*/, int reset) {
     if (!e) e = (int)cudaStreamSynchronize(s2);
     cudaStreamDestroy(s2);
     return e;
-}
-#endif
-#ifdef LV_WATCHDOG
-extern "C" int lv_debug_watchdog(unsigned long long* out) {   /* out[8]; [0] = id of the first loop that ran away (0: none) */
-    cudaDeviceSynchronize();
-    return (int)cudaMemcpyFromSymbol(out, g_lv_wd, sizeof(unsigned long long) * 8);
 }
 #endif
 #ifdef LV_STEP_TIMING

@@ -35,7 +35,7 @@ extern "C" void lv_default_params(lv_params* p) {
      * rotation is unusable, identity is the neutral choice here */
     p->I_Rotation_L[0] = p->I_Rotation_L[4] = p->I_Rotation_L[8] = 1.f;
     p->map_downsample_size = 0.2f;            /* Mapper.cpp:65 */
-    p->voxel_size = 0.5f;
+    p->voxel_size = 0.4f;
     p->device = 0;
     p->sort_queries = 0;
     p->max_map_points = 4 * 1024 * 1024;

@@ -7,8 +7,8 @@
  * the very code the kernels run against the oracle, in a container without a GPU.
  *
  * It is NOT part of the product, is not linked into liblimovelo_b200.so and is not reachable from
- * the C ABI; the product has no CPU path.  The hash-table builder below is a plain host loop that
- * produces the same layout lv_map_build.cu produces on the device.
+ * the C ABI; the product has no CPU path.  The map is built and updated by the product's own per-item functions
+ * (lv_voxel_map.h), called from plain host loops in the order lv_map.cu launches its kernels.
  */
 #include <stdint.h>
 #include <string.h>
@@ -23,10 +23,12 @@
 using namespace lv;
 
 struct ShimMap {
-    std::vector<float4> pts;
-    std::vector<float4> halo;
-    std::vector<uint4> table[kMaxLevels];
+    std::vector<uint4> table, btable;
+    std::vector<float4> arena;
+    std::vector<uint32_t> counters, touched, dirty;
+    VoxelMapRW rw;
     VoxelMapView view;
+    uint32_t n_inserted = 0;
 };
 
 struct ShimParams {
@@ -41,109 +43,108 @@ struct ShimParams {
 
 extern "C" {
 
-static void shim_insert(std::vector<uint4>& tab, uint32_t mask, uint64_t key, uint32_t start, uint32_t count, bool only_if_absent) {
-    uint32_t slot = voxel_hash(key) & mask;
-    for (;;) {
-        uint4& t = tab[2 * (size_t)slot];
-        if ((t.x & t.y) == 0xFFFFFFFFu) { t.x = (uint32_t)key; t.y = (uint32_t)(key >> 32); t.z = start; t.w = count; return; }
-        if (only_if_absent && t.x == (uint32_t)key && t.y == (uint32_t)(key >> 32)) return;
-        slot = (slot + 1) & mask;
+/* the product's map update (lv_voxel_map.h: map_point_key, map_merge_run, map_dilate_item, map_halo_voxel_serial) run
+ * serially, in the order lv_map.cu launches the kernels: keys -> stable sort -> merge -> dilate -> halo */
+static void shim_add_impl(ShimMap* sm, const float* xyz, int64_t n, int downsample) {
+    VoxelMapRW& m = sm->rw;
+    m.counters[kCtrTouched] = 0;
+    m.counters[kCtrDirty] = 0;
+    std::vector<uint32_t> keys(n), vals(n);
+    for (int64_t i = 0; i < n; ++i) { keys[i] = map_point_key(m, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]); vals[i] = (uint32_t)i; }
+    std::stable_sort(vals.begin(), vals.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+    std::vector<uint32_t> ks(n);
+    for (int64_t j = 0; j < n; ++j) ks[j] = keys[vals[j]];
+    for (int64_t j = 0; j < n; ++j) {
+        if (ks[j] == 0xFFFFFFFFu) continue;
+        if (j > 0 && (ks[j - 1] >> kCellBits) == (ks[j] >> kCellBits)) continue;
+        map_merge_run(m, ks.data(), vals.data(), (uint32_t)j, (uint32_t)n, xyz, sm->n_inserted, downsample);
     }
+    const uint32_t nt = m.counters[kCtrTouched];
+    for (uint32_t t = 0; t < nt * 27u; ++t) map_dilate_item(m, m.touched[t / 27u], (int)(t % 27u));
+    const uint32_t nd = m.counters[kCtrDirty];
+    for (uint32_t d = 0; d < nd; ++d) map_halo_voxel_serial(m, m.dirty[d]);
+    sm->n_inserted += (uint32_t)n;
 }
 
-/* host construction of exactly the layout lv_map_build.cu produces: Morton-sorted points, per level
- * a 32-byte-slot hash table; level 0 dilated by one voxel and with halo buckets (own points first,
- * then neighbours 0..26) */
 ShimMap* shim_map_create(const float* xyz, int64_t m, float cell, double max_dist) {
+    (void)max_dist;
     ShimMap* sm = new ShimMap();
-    const float inv = 1.0f / cell;
-    std::vector<uint64_t> keys(m);
-    for (int64_t i = 0; i < m; ++i)
-        keys[i] = morton3(voxel_coord(xyz[3 * i], inv), voxel_coord(xyz[3 * i + 1], inv), voxel_coord(xyz[3 * i + 2], inv));
-    std::vector<uint32_t> order(m);
-    std::iota(order.begin(), order.end(), 0u);
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
-    sm->pts.resize(m);
-    std::vector<uint64_t> ks(m);
-    for (int64_t j = 0; j < m; ++j) {
-        const uint32_t s = order[j];
-        float4 p;
-        p.x = xyz[3 * s]; p.y = xyz[3 * s + 1]; p.z = xyz[3 * s + 2];
-        int32_t si = (int32_t)s;
-        memcpy(&p.w, &si, 4);
-        sm->pts[j] = p;
-        ks[j] = keys[s];
-    }
-    int n_levels = 1;
-    while (n_levels < kMaxLevels && (double)cell * (double)(1 << (n_levels - 1)) < max_dist) n_levels++;
-    sm->view.pts = sm->pts.data();
-    sm->view.n_levels = n_levels;
-    sm->view.n_points = (uint32_t)m;
-    sm->view.cell0 = cell;
-    sm->view.inv_cell0 = inv;
-    for (int l = 0; l < n_levels; ++l) {
-        std::vector<uint4>& tab = sm->table[l];
-        int64_t heads = 0;
-        for (int64_t j = 0; j < m; ++j)
-            if (j == 0 || (ks[j - 1] >> (3 * l)) != (ks[j] >> (3 * l))) ++heads;
-        uint32_t slots = 1024;
-        while (slots < (l == 0 ? 10 : 2) * heads) slots <<= 1;
-        uint4 empty; empty.x = empty.y = 0xFFFFFFFFu; empty.z = empty.w = 0;
-        uint4 zero; zero.x = zero.y = zero.z = zero.w = 0;
-        tab.assign(2 * (size_t)slots, zero);
-        for (uint32_t s = 0; s < slots; ++s) tab[2 * (size_t)s] = empty;
-        const uint32_t mask = slots - 1;
-        for (int64_t j = 0; j < m;) {
-            const uint64_t key = ks[j] >> (3 * l);
-            int64_t e = j + 1;
-            while (e < m && (ks[e] >> (3 * l)) == key) ++e;
-            shim_insert(tab, mask, voxel_key_from_morton(ks[j], l), (uint32_t)j, (uint32_t)(e - j), false);
-            j = e;
-        }
-        if (l == 0) {   /* dilation: empty neighbours of occupied voxels get a slot with count 0 */
-            for (int64_t j = 0; j < m; ++j) {
-                if (j > 0 && ks[j - 1] == ks[j]) continue;
-                const int bx = (int)compact21(ks[j]), by = (int)compact21(ks[j] >> 1), bz = (int)compact21(ks[j] >> 2);
-                for (int nb = 0; nb < 27; ++nb) {
-                    const int cx = bx + nb % 3 - 1, cy = by + (nb / 3) % 3 - 1, cz = bz + nb / 9 - 1;
-                    if (nb == 13 || cx < 0 || cy < 0 || cz < 0 || cx > 0x1FFFFF || cy > 0x1FFFFF || cz > 0x1FFFFF) continue;
-                    shim_insert(tab, mask, voxel_key((uint32_t)cx, (uint32_t)cy, (uint32_t)cz), 0, 0, true);
-                }
-            }
-        }
-        VoxelLevel& L = sm->view.lv[l];
-        L.table = tab.data();
-        L.mask = mask;
-        L.cell = cell * (float)(1 << l);
-    }
-    {   /* level-0 halo buckets */
-        std::vector<uint4>& tab = sm->table[0];
-        const VoxelLevel& L = sm->view.lv[0];
-        for (uint32_t s = 0; s <= L.mask; ++s) {
-            const uint4 t = tab[2 * (size_t)s];
-            if ((t.x & t.y) == 0xFFFFFFFFu) continue;
-            const uint64_t key = ((uint64_t)t.y << 32) | t.x;
-            const int bx = (int)(key & 0x1FFFFFu), by = (int)((key >> 21) & 0x1FFFFFu), bz = (int)((key >> 42) & 0x1FFFFFu);
-            const uint32_t base = (uint32_t)sm->halo.size();
-            for (int lane = 0; lane < 27; ++lane) {
-                const int nb = lane == 0 ? 13 : (lane <= 13 ? lane - 1 : lane);
-                const int cx = bx + nb % 3 - 1, cy = by + (nb / 3) % 3 - 1, cz = bz + nb / 9 - 1;
-                uint32_t st, cn;
-                if (cx < 0 || cy < 0 || cz < 0) continue;
-                if (voxel_find(L, voxel_key((uint32_t)cx, (uint32_t)cy, (uint32_t)cz), &st, &cn) < 0) continue;
-                for (uint32_t k = 0; k < cn; ++k) sm->halo.push_back(sm->pts[st + k]);
-            }
-            tab[2 * (size_t)s + 1].x = base;
-            tab[2 * (size_t)s + 1].y = (uint32_t)sm->halo.size() - base;
-        }
-        sm->view.halo = sm->halo.data();
-    }
-    for (int l = n_levels; l < kMaxLevels; ++l) sm->view.lv[l] = sm->view.lv[0];
+    const float ds = 0.2f;
+    int k = (int)floor((double)cell / (double)ds + 0.5);
+    k = k < 1 ? 1 : (k > kMaxCellsPerVoxel ? kMaxCellsPerVoxel : k);
+    uint32_t slots = 1u << 14;
+    while (slots < 8 * (uint64_t)(m + 65536)) slots <<= 1;
+    uint4 empty; empty.x = empty.y = 0xFFFFFFFFu; empty.z = empty.w = 0;
+    uint4 zero; zero.x = zero.y = zero.z = zero.w = 0;
+    sm->table.assign(2 * (size_t)slots, zero);
+    for (uint32_t s = 0; s < slots; ++s) sm->table[2 * (size_t)s] = empty;
+    sm->btable.assign(slots / 4, empty);
+    sm->arena.resize((size_t)64 * (size_t)(m + 65536) + (1u << 20));
+    sm->counters.assign(kMapCounters, 0u);
+    sm->counters[kCtrArenaTop] = 16u;
+    sm->touched.resize(slots);
+    sm->dirty.resize(slots);
+    VoxelMapRW& r = sm->rw;
+    r.table = sm->table.data(); r.mask = slots - 1; r.btable = sm->btable.data(); r.bmask = slots / 4 - 1;
+    r.arena = sm->arena.data(); r.arena_cap = (uint32_t)sm->arena.size(); r.counters = sm->counters.data();
+    r.touched = sm->touched.data(); r.dirty = sm->dirty.data(); r.list_cap = slots;
+    r.grid.ds = ds; r.grid.k = k; r.grid.cell0 = (float)k * ds;
+    sm->view = map_view_of(r);
+    if (m > 0) shim_add_impl(sm, xyz, m, 0);
     return sm;
+}
+/* Mapper::add on an existing map (KD_TREE::Add_Points) */
+void shim_map_add(ShimMap* sm, const float* xyz, int64_t n, int downsample) { shim_add_impl(sm, xyz, n, downsample); }
+int64_t shim_map_size(const ShimMap* sm) { return (int64_t)(int32_t)sm->counters[kCtrPoints]; }
+uint32_t shim_map_error(const ShimMap* sm) { return sm->counters[kCtrError]; }
+/* all points, ascending id (insertion order) */
+int64_t shim_map_points(const ShimMap* sm, float* out, int64_t cap) {
+    std::vector<float4> all;
+    for (uint32_t s = 0; s <= sm->rw.mask; ++s) {
+        const uint4 t = sm->table[2 * (size_t)s];
+        if ((t.x & t.y) == 0xFFFFFFFFu) continue;
+        for (uint32_t k = 0; k < t.w; ++k) all.push_back(sm->arena[t.z + k]);
+    }
+    std::sort(all.begin(), all.end(), [](const float4& a, const float4& b) { uint32_t ia, ib; memcpy(&ia, &a.w, 4); memcpy(&ib, &b.w, 4); return ia < ib; });
+    const int64_t n = (int64_t)all.size() < cap ? (int64_t)all.size() : cap;
+    for (int64_t i = 0; i < n; ++i) { out[3 * i] = all[i].x; out[3 * i + 1] = all[i].y; out[3 * i + 2] = all[i].z; }
+    return (int64_t)all.size();
+}
+/* structural invariants of the layout (tests): every halo bucket equals the concatenation of the 27 own extents */
+int shim_map_check(const ShimMap* sm) {
+    const VoxelMapRW& m = sm->rw;
+    for (uint32_t s = 0; s <= m.mask; ++s) {
+        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(m.table + 2 * (size_t)s);
+        if ((s32[0] & s32[1]) == 0xFFFFFFFFu) continue;
+        if (s32[7] != 0u) return 1;                                         /* dirty flag left set */
+        if (s32[3] > caps_own(s32[6]) || s32[5] > caps_halo(s32[6])) return 2;
+        const uint64_t key = (uint64_t)s32[0] | ((uint64_t)s32[1] << 32);
+        const int bx = (int)((uint32_t)key & 0x1FFFFFu), by = (int)((uint32_t)(key >> 21) & 0x1FFFFFu), bz = (int)((uint32_t)(key >> 42) & 0x1FFFFFu);
+        uint32_t w = s32[4], total = 0;
+        bool any_occupied_nb = false;
+        for (int l = 0; l < 27; ++l) {
+            const int nb = halo_lane_to_nb(l);
+            const int cx = bx + nb % 3 - 1, cy = by + (nb / 3) % 3 - 1, cz = bz + nb / 9 - 1;
+            if (cx < 0 || cy < 0 || cz < 0) continue;
+            const int ns = voxel_find_rw(m, voxel_key((uint32_t)cx, (uint32_t)cy, (uint32_t)cz));
+            if (ns < 0) { if (s32[3] > 0) return 3; continue; }             /* an occupied voxel has all 26 neighbour slots */
+            const uint32_t* n32 = reinterpret_cast<const uint32_t*>(m.table + 2 * (size_t)ns);
+            any_occupied_nb = any_occupied_nb || n32[3] > 0;
+            for (uint32_t t = 0; t < n32[3]; ++t, ++w)
+                if (memcmp(&m.arena[w], &m.arena[n32[2] + t], sizeof(float4)) != 0) return 4;
+            total += n32[3];
+        }
+        if (total != s32[5]) return 5;
+        if (s32[3] > 0) {                                                   /* block occupancy bit */
+            if (!((block_find(sm->view, voxel_key((uint32_t)bx >> 2, (uint32_t)by >> 2, (uint32_t)bz >> 2)) >> block_bit((uint32_t)bx, (uint32_t)by, (uint32_t)bz)) & 1ull)) return 6;
+        }
+    }
+    return 0;
 }
 void shim_map_destroy(ShimMap* m) { delete m; }
 
 static void search_setup(const ShimParams* p, float cell, float* max_d2, double* gate, int* max_ring) {
+    (void)cell;
     *gate = p->max_dist_plane * p->max_dist_plane;
     float f = (float)*gate;
     if ((double)f < *gate) f = nextafterf(f, INFINITY);
@@ -159,18 +160,17 @@ void shim_match_all(const ShimMap* sm, const double* x, const ShimParams* p, con
     Frame fr;
     make_frame(x, &fr);
     float max_d2; double gate; int max_ring;
-    search_setup(p, sm->view.cell0, &max_d2, &gate, &max_ring);
+    search_setup(p, sm->view.grid.cell0, &max_d2, &gate, &max_ring);
     for (int64_t i = 0; i < n; ++i) {
         float g[3];
         rt_apply(fr.lidar_to_world, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], g);
         Top5 t;
-        const float4* src = sm->view.halo;                     /* the two phases of lv_measure_kernel */
+        const float4* src = sm->view.arena;                    /* the two tiers of the search kernels */
         uint32_t bs, bc;
-        const bool has_bucket = level0_probe(sm->view, g[0], g[1], g[2], &bs, &bc);
+        const bool has_bucket = level0_probe(sm->view, g[0], g[1], g[2], &bs, &bc) >= 0;
         if (!level0_scan<GroupSerial>(sm->view, g[0], g[1], g[2], max_d2, bs, bc, has_bucket, t)) {
             const float bound0 = t.i4 >= 0 ? t.d4 : max_d2;
-            knn5_upper<GroupSerial>(sm->view, g[0], g[1], g[2], max_d2, bound0, t);
-            src = sm->view.pts;
+            knn5_rings<GroupSerial>(sm->view, g[0], g[1], g[2], max_d2, bound0, t);
         }
         float abcd[4] = {0, 0, 0, 0}, d = 0;
         double row[12] = {0}, h = 0;
@@ -313,15 +313,15 @@ extern "C" void shim_reuse_check(const ShimMap* sm, const double* x0, const doub
     auto search = [&](const float* g, Top5& t, float* lb) -> const float4* {
         uint32_t bs, bc;
         float region = 0.f;
-        const bool hb = level0_probe(sm->view, g[0], g[1], g[2], &bs, &bc);
+        const bool hb = level0_probe(sm->view, g[0], g[1], g[2], &bs, &bc) >= 0;
         if (level0_scan<GroupSerial>(sm->view, g[0], g[1], g[2], max_d2, bs, bc, hb, t, &region)) {
             *lb = outsider_bound(t.d5, region);
-            return sm->view.halo;
+            return sm->view.arena;
         }
         const float bound0 = t.i4 >= 0 ? t.d4 : max_d2;
-        knn5_upper<GroupSerial>(sm->view, g[0], g[1], g[2], max_d2, bound0, t, &region);
+        knn5_rings<GroupSerial>(sm->view, g[0], g[1], g[2], max_d2, bound0, t, &region);
         *lb = outsider_bound(t.d5, region);
-        return sm->view.pts;
+        return sm->view.arena;
     };
     for (int64_t i = 0; i < n; ++i) {
         float g0[3], g1[3];
@@ -366,12 +366,9 @@ extern "C" void shim_query_stats(const ShimMap* sm, const double* x, const float
         rt_apply(fr.lidar_to_world, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], g);
         Top5 t;
         uint32_t bs, bc;
-        const bool hb = level0_probe(sm->view, g[0], g[1], g[2], &bs, &bc);
-        const bool ok = level0_scan<GroupSerial>(sm->view, g[0], g[1], g[2], max_d2, bs, bc, hb, t);
-        uint32_t s, c;
-        const int slot = voxel_find(sm->view.lv[0], voxel_key(voxel_coord(g[0], sm->view.inv_cell0), voxel_coord(g[1], sm->view.inv_cell0),
-                                                              voxel_coord(g[2], sm->view.inv_cell0)), &s, &c);
+        const int slot = level0_probe(sm->view, g[0], g[1], g[2], &bs, &bc);
+        const bool ok = level0_scan<GroupSerial>(sm->view, g[0], g[1], g[2], max_d2, bs, bc, slot >= 0, t);
         level_out[i] = ok ? 0 : (slot < 0 ? 2 : 1);    /* 0 settled, 1 bucket but not certified, 2 no slot */
-        scanned_out[i] = slot >= 0 ? (int)sm->view.lv[0].table[2 * (size_t)slot + 1].y : 0;
+        scanned_out[i] = slot >= 0 ? (int)bc : 0;
     }
 }

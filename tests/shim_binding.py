@@ -32,6 +32,14 @@ def lib():
         L.shim_map_create.restype = C.c_void_p
         L.shim_map_create.argtypes = [C.POINTER(C.c_float), C.c_int64, C.c_float, C.c_double]
         L.shim_map_destroy.argtypes = [C.c_void_p]
+        L.shim_map_add.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int64, C.c_int]
+        L.shim_map_size.argtypes = [C.c_void_p]
+        L.shim_map_size.restype = C.c_int64
+        L.shim_map_error.argtypes = [C.c_void_p]
+        L.shim_map_error.restype = C.c_uint32
+        L.shim_map_points.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int64]
+        L.shim_map_points.restype = C.c_int64
+        L.shim_map_check.argtypes = [C.c_void_p]
         assert L.shim_sizeof_iterlog() == C.sizeof(IterLog)
         _lib = L
     return _lib
@@ -71,6 +79,28 @@ class ShimMap:
             self.L.shim_map_destroy(C.c_void_p(self.h))
         except Exception:
             pass
+
+    def add(self, xyz, downsample=True):
+        """Mapper::add on an existing map (KD_TREE::Add_Points), through the product's map_merge_run / dilate / halo"""
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        self.L.shim_map_add(C.c_void_p(self.h), _f(xyz), xyz.shape[0], int(downsample))
+
+    def size(self):
+        return int(self.L.shim_map_size(C.c_void_p(self.h)))
+
+    def error(self):
+        return int(self.L.shim_map_error(C.c_void_p(self.h)))
+
+    def points(self):
+        n = self.size()
+        out = np.zeros((max(n, 1), 3), np.float32)
+        k = self.L.shim_map_points(C.c_void_p(self.h), _f(out), n)
+        assert k == n
+        return out[:n]
+
+    def check(self):
+        """0 when every halo bucket equals the concatenation of its 27 own extents, flags are clear, blocks are marked"""
+        return int(self.L.shim_map_check(C.c_void_p(self.h)))
 
     def match_all(self, x, prm, xyz, rows=False):
         xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)

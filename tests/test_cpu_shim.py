@@ -165,3 +165,69 @@ def test_neighbour_reuse_is_exact(O, scene_xaloc, cell):
             d[0:3] = mv
             reused, same = sm.reuse_check(sc.x_prop, O.boxplus(sc.x_prop, d), q, sc.prm.MAX_DIST_PLANE)
             assert same[reused].all()
+
+
+def _world(sweep, x, O):
+    R = O.quat_to_rot(x[3:7]); RL = O.quat_to_rot(x[7:11])
+    return ((sweep.astype(np.float64) @ RL.T + x[11:14]) @ R.T + x[0:3]).astype(np.float32)
+
+
+@pytest.mark.parametrize("cell", [0.4, 0.2, 0.6])
+def test_incremental_map_add_matches_reference_rule(O, scene_xaloc, cell):
+    """Mapper::add = KD_TREE::Add_Points with the 0.2 m rule (ikd_Tree.cpp:478-573), three sweeps streamed into the map by
+    the product's incremental update (map_point_key -> sort -> map_merge_run -> dilate -> halo): the content equals the
+    oracle's (and the reference ikd-Tree's), the layout invariants hold, and searching the UPDATED map is still exact."""
+    sc = scene_xaloc
+    sm = S.ShimMap(sc.map, cell, 2.0)
+    assert sm.size() == len(sc.map) and sm.check() == 0 and sm.error() == 0
+    assert (sm.points() == sc.map).all()                            # Build keeps every point, insertion order
+    backends = [O.KNN_KDTREE] + ([O.KNN_REF_IKDTREE] if O.ref_available() else [])
+    oms = []
+    for be in backends:
+        om = O.Map(be)
+        om.build(sc.map)
+        oms.append(om)
+    rng = np.random.default_rng(3)
+    for k in range(3):
+        x = sc.truth.copy()
+        x[0:3] += [1.5 * k, 0.2 * k, 0.0]
+        new = _world(sc.sweep, x, O) + rng.normal(0, 0.01, (len(sc.sweep), 3)).astype(np.float32)
+        sm.add(new, downsample=True)
+        assert sm.check() == 0 and sm.error() == 0
+        got = set(map(tuple, sm.points().tolist()))
+        assert len(got) == sm.size()
+        for om in oms:
+            om.add(new, downsample=True)
+            ref = set(map(tuple, om.points().tolist()))
+            assert len(got ^ ref) <= 1e-4 * len(ref), (k, len(got ^ ref), len(ref))     # voxel-face ulp cases
+    # the updated map answers queries exactly like a kd-tree over the same points
+    om = O.Map(O.KNN_KDTREE)
+    om.build(sm.points())
+    q = sc.sweep[::7]
+    ref = om.match_all(sc.x_prop, sc.oprm, q)
+    got = sm.match_all(sc.x_prop, S.make_params(sc.oprm, cell), q)
+    inside = np.isfinite(got["nn_sqd"][:, 4])
+    assert not (ref["nn_sqd"][~inside, 4].astype(np.float64) < 4.0).any()
+    assert (got["nn_sqd"][inside] == ref["nn_sqd"][inside]).all()
+    assert (got["valid"] == ref["valid"]).all() and (got["plane"] == ref["plane"]).all()
+
+
+def test_incremental_map_without_downsampling_and_scattered_points(O):
+    """Add_Points(..., downsample = false) appends; isolated random points (27 slots each) neither hang nor corrupt"""
+    rng = np.random.default_rng(11)
+    a = rng.uniform(-40, 40, (3000, 3)).astype(np.float32)          # every point alone in its voxel
+    b = rng.uniform(-40, 40, (2000, 3)).astype(np.float32)
+    sm = S.ShimMap(a, 0.4, 2.0)
+    sm.add(b, downsample=False)
+    assert sm.size() == 5000 and sm.check() == 0 and sm.error() == 0
+    assert (sm.points() == np.concatenate([a, b])).all()
+    om = O.Map(O.KNN_KDTREE)
+    om.build(np.concatenate([a, b]))
+    x = np.zeros(26); x[6] = 1; x[10] = 1; x[23] = 9.809
+    prm = O.make_params()
+    q = rng.uniform(-40, 40, (2000, 3)).astype(np.float32)
+    ref = om.match_all(x, prm, q)
+    got = sm.match_all(x, S.make_params(prm, 0.4), q)
+    inside = np.isfinite(got["nn_sqd"][:, 4])
+    assert not (ref["nn_sqd"][~inside, 4].astype(np.float64) < 4.0).any()
+    assert (got["nn_sqd"][inside] == ref["nn_sqd"][inside]).all()

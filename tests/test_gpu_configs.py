@@ -1,0 +1,88 @@
+"""BASELINE.json configs 0, 2 and 3 at their full sizes on the GPU, against the oracle (kNN = the reference's own
+ikd_Tree.cpp where oracle/_ref is present): 65 536 points vs a 100 k planar map with a single evaluation; KITTI-shape
+131 072-point sweeps cut into ten 13 107-point sub-sweeps vs a 5 M map (kitti.yaml); Ouster-128 262 144 points vs a
+10 M map (ouster.yaml).  cfg1 lives in test_gpu_fullsize.py."""
+import numpy as np
+import pytest
+
+import bench
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(1500, method="thread")]
+
+
+def _setup(lv, O, cfg, n_sweeps):
+    prm = bench.config_params(lv, cfg)
+    world, mp, sweeps, x_props, truths = bench.make_scene(lv, 0, n_sweeps=n_sweeps, prm=prm, cfg=cfg)
+    loc = lv.Localizer(prm)
+    loc.map_build(mp)
+    loc.map_status()
+    assert loc.map_size() == len(mp) == bench.CONFIGS[cfg]["map_points"]
+    om = O.Map(O.KNN_REF_IKDTREE if O.ref_available() else O.KNN_KDTREE)
+    om.build(mp)
+    x0, P0 = lv.init_state_host(prm)
+    return prm, loc, om, sweeps, x_props, truths, P0, bench.oracle_params(O, prm)
+
+
+def _check_update(loc, om, oprm, x_prop, P0, sweep, O, min_matches):
+    loc.set_state(x_prop, P0)
+    st, x, P, logs = loc.correct(sweep)
+    st_o, x_o, P_o, logs_o = om.update_iterated(x_prop, P0, oprm, sweep)
+    assert st == st_o == 0 and len(logs) == len(logs_o)
+    for k, (a, b) in enumerate(zip(logs, logs_o)):
+        assert a["n_matches"] == b["n_matches"] > min_matches, (k, a["n_matches"], b["n_matches"])
+        assert np.abs(a["HTH"] - b["HTH"]).max() <= (1e-12 if k == 0 else 1e-8) * np.abs(b["HTH"]).max()
+        assert np.abs(a["dx"] - b["dx"]).max() < (1e-9 if k == 0 else 1e-7), (k, np.abs(a["dx"] - b["dx"]).max())
+    assert np.abs(x - x_o).max() < 1e-7
+    assert np.abs(P - P_o).max() <= 1e-6 * np.abs(P_o).max()
+    return x, logs
+
+
+def _check_points(loc, om, oprm, x_prop, sweep):
+    got = loc.match_all(x_prop, sweep)
+    ref = om.match_all(x_prop, oprm, sweep)
+    inside = np.isfinite(got["nn_sqd"][:, 4])
+    assert not (ref["nn_sqd"][~inside, 4].astype(np.float64) < oprm.max_dist_plane ** 2).any()
+    assert (got["nn_sqd"][inside] == ref["nn_sqd"][inside]).all()
+    assert (got["valid"] == ref["valid"]).all() and (got["plane"] == ref["plane"]).all() and (got["dist"] == ref["dist"]).all()
+    return got
+
+
+def test_cfg0_planar_map_single_evaluation(lv, O):
+    prm, loc, om, sweeps, x_props, truths, P0, oprm = _setup(lv, O, "cfg0", 2)
+    assert prm.MAX_NUM_ITERS == 0
+    for k in range(2):
+        x, logs = _check_update(loc, om, oprm, x_props[k], P0, sweeps[k], O, 40000)
+        assert len(logs) == 1                                       # I forced to 1 (esekfom.hpp:1634 with max_iter = 0)
+        err = np.abs(O.boxminus(x, truths[k]))
+        assert err[2] < 5e-3 and err[3:5].max() < 2e-3              # a plane observes z, roll, pitch only
+    got = _check_points(loc, om, oprm, x_props[0], sweeps[0])
+    assert got["valid"].mean() > 0.8
+    loc.close()
+
+
+def test_cfg2_kitti_subsweeps_5m_map(lv, O):
+    prm, loc, om, sweeps, x_props, truths, P0, oprm = _setup(lv, O, "cfg2", 1)
+    assert prm.estimate_extrinsics == 0 and abs(prm.MAX_DIST_PLANE - 2.23) < 1e-12
+    assert len(sweeps) == 10 and all(len(s) == 13107 for s in sweeps)
+    for k in range(10):
+        x, logs = _check_update(loc, om, oprm, x_props[k], P0, sweeps[k], O, 8000)
+        for a in logs:                                              # extrinsics not estimated: columns 6..11 of every row are zero
+            assert (a["HTH"][6:, :] == 0).all() and (a["HTH"][:, 6:] == 0).all()
+    for k in (0, 9):
+        _check_points(loc, om, oprm, x_props[k], sweeps[k])
+    loc.close()
+
+
+def test_cfg3_ouster_10m_map(lv, O):
+    prm, loc, om, sweeps, x_props, truths, P0, oprm = _setup(lv, O, "cfg3", 1)
+    x, logs = _check_update(loc, om, oprm, x_props[0], P0, sweeps[0], O, 200000)
+    err = np.abs(O.boxminus(x, truths[0]))
+    assert err[:3].max() < 5e-3 and err[3:6].max() < 5e-4
+    _check_points(loc, om, oprm, x_props[0], sweeps[0])
+    # Mapper::add at this size: the sweep, in world coordinates, goes into the 10 M map on the device
+    g = bench.world_points(sweeps[0], x)
+    loc.map_add(g, downsample=True)
+    om.add(g, downsample=True)
+    loc.map_status()
+    assert abs(loc.map_size() - om.size()) <= 1e-5 * om.size()
+    loc.close()
