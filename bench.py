@@ -290,6 +290,8 @@ def run_native(args, rank, local_rank, world_size):
     prm = config_params(lv, cfg, device=local_rank, stream=stream.cuda_stream)
     if args.voxel:                                                  # tuning runs only; the default is the library's
         prm.voxel_size = args.voxel
+    if args.sort_queries is not None:
+        prm.sort_queries = args.sort_queries
     world, mp, sweeps, x_props, truths = make_scene(lv, rank, prm=prm, cfg=cfg)
     n = sweeps[0].shape[0]
     loc = lv.Localizer(prm)
@@ -378,6 +380,34 @@ def run_native(args, rank, local_rank, world_size):
         loc.synchronize()
         t_add.append(time.perf_counter() - t0)
 
+    # ---- per sweep on the device: update + Mapper::add (main.cpp:84-105), nothing visits the host in between.
+    # It changes the map, so it runs after the headline's timed regions (which replay sweeps against a fixed map). ----
+    per_sweep = None
+    try:
+        ps_steps = min(args.steps, 100)
+        ps_ms, ps_upd_ms, ps_evals = 0.0, 0.0, 0
+        for i in range(ps_steps):
+            j = (args.warmup + i) % len(sweeps)
+            loc.set_state(x_props[j], P0)
+            ea, eb, ec = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            ea.record(stream)
+            loc.correct_device(d_sweeps[j], n)
+            eb.record(stream)
+            loc.map_add_last_sweep(True)                            # sweep -> world with the update's own result -> 0.2 m rule -> halo buckets
+            ec.record(stream)
+            st, lg = loc.last_logs()
+            ps_ms += ea.elapsed_time(ec)
+            ps_upd_ms += ea.elapsed_time(eb)
+            ps_evals += len(lg)
+            loc.flush_l2()
+        loc.map_status()
+        per_sweep = {"ms": ps_ms / ps_steps, "update_ms": ps_upd_ms / ps_steps, "map_add_ms": (ps_ms - ps_upd_ms) / ps_steps,
+                     "point_evaluations_per_s": n * ps_evals / (ps_ms * 1e-3), "sweeps": ps_steps, "map_points_after": loc.map_size(),
+                     "how": "lv_correct_device + lv_map_add_last_sweep per sweep, CUDA events on the library's stream, L2 flushed between sweeps; "
+                            "the map grows by the sweep's new cells"}
+    except Exception as e:
+        per_sweep = {"error": str(e)}
+
     # ---- deskew (Compensator::compensate), reported beside the headline ----
     deskew = None
     try:
@@ -434,6 +464,14 @@ def run_native(args, rank, local_rank, world_size):
                       "lv_temporal_downsample_host_ms": 1e3 * dt_td, "note": "blocking calls, wall clock"}
     except Exception as e:
         downsample = {"error": str(e)}
+
+    # ---- several sequences per GPU (one update does not fill a B200): S handles on S streams, one step = S concurrent updates ----
+    multi = None
+    if args.sequences_per_gpu:
+        try:
+            multi = multi_sequence_leg(lv, torch, cfg, local_rank, rank, [int(v) for v in args.sequences_per_gpu.split(",")], min(args.steps, 200))
+        except Exception as e:
+            multi = {"error": str(e)}
 
     # ---- max over ranks / totals ----
     tot = torch.tensor([step_ms, float(pts), float(matched), e2e_s, float(e2e_pts), float(launches)],
@@ -500,7 +538,10 @@ def run_native(args, rank, local_rank, world_size):
                          "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
                          "kernel": dominant, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_POINT * n},
             "cpu_baseline": cpu,
-            "map_update": {"lv_map_add_ms": 1e3 * min(t_add), "points_added": n, "map_points": loc.map_size()},
+            "per_sweep": per_sweep,
+            "map_update": {"lv_map_add_ms": 1e3 * min(t_add), "points_added": n, "map_points": loc.map_size(),
+                           "how": "lv_map_add() from a pageable host buffer, wall clock incl. the H2D copy and a stream synchronisation"},
+            "multi_sequence": multi,
             "deskew": deskew, "downsample": downsample,
             "final_position_error_m": pose_err,
             "clocks": clock_info,
@@ -511,6 +552,63 @@ def run_native(args, rank, local_rank, world_size):
     loc.close()
     if world_size > 1:
         dist.destroy_process_group()
+
+
+def multi_sequence_leg(lv, torch, cfg, local_rank, rank, s_list, steps):
+    """point-evaluations/s of ONE GPU running S independent sequences at once (S handles, S streams, no shared state)"""
+    out = []
+    n = update_points(cfg)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for S in s_list:
+        streams = [torch.cuda.Stream() for _ in range(S)]
+        locs, data = [], []
+        for s in range(S):
+            prm = config_params(lv, cfg, device=local_rank, stream=streams[s].cuda_stream)
+            world, mp, sweeps, x_props, truths = make_scene(lv, 50 + 8 * rank + s, n_sweeps=4, prm=prm, cfg=cfg)
+            loc = lv.Localizer(prm)
+            loc.map_build(mp)
+            loc.init_state()
+            _, P0 = loc.get_state()
+            locs.append(loc)
+            data.append(([loc.upload(sw) for sw in sweeps], x_props, P0))
+
+        def step(i, timed):
+            for s in range(S):
+                locs[s].set_state(data[s][1][i % 4], data[s][2])
+            fork, join = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(streams[0]):
+                flush.fill_(i & 255)                                # L2 flush between steps
+            fork.record(streams[0])
+            ends = []
+            for s in range(S):
+                if s:
+                    streams[s].wait_event(fork)
+                locs[s].correct_device(data[s][0][i % 4], n)
+                e = torch.cuda.Event()
+                e.record(streams[s])
+                ends.append(e)
+            for e in ends[1:]:
+                streams[0].wait_event(e)
+            join.record(streams[0])
+            evals = sum(len(locs[s].last_logs()[1]) for s in range(S))   # synchronises each stream
+            return fork.elapsed_time(join), evals
+        for i in range(3):
+            step(i, False)
+        ms, evals = 0.0, 0
+        for i in range(steps):
+            m, e = step(3 + i, True)
+            ms += m
+            evals += e
+        out.append({"sequences": S, "ms_per_step": ms / steps, "point_evaluations_per_s": n * evals / (ms * 1e-3)})
+        for loc in locs:
+            loc.close()
+        del locs, data
+        torch.cuda.empty_cache()
+    base = out[0]["point_evaluations_per_s"] if out and out[0]["sequences"] == 1 else None
+    for o in out:
+        o["vs_one_sequence"] = o["point_evaluations_per_s"] / base if base else None
+    return {"how": "S independent handles on S CUDA streams of one GPU; one step = S concurrent updates, fork/join CUDA events, "
+                   "L2 flushed between steps", "results": out}
 
 
 def deskew_case(lv, world, prm, sweep, t1=10.0, t2=10.1, n_states=4, imu_hz=400.0):
@@ -549,6 +647,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--config", default="cfg1", choices=sorted(CONFIGS), help="BASELINE.json config (default cfg1 = the metric's)")
+    ap.add_argument("--sequences-per-gpu", default="", help="e.g. 1,2,4,8: also measure S concurrent sequences per GPU (multi_sequence)")
+    ap.add_argument("--sort-queries", type=int, default=None, help="tuning: 1 = binned order + search from shared memory, 0 = per-query search")
     ap.add_argument("--voxel", type=float, default=0.0, help="tuning: finest voxel edge of the map (0 = library default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

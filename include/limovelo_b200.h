@@ -146,6 +146,13 @@ int64_t lv_map_points(lv_handle h, float* xyz_out, int64_t cap);
  * until the stream has passed the call.                                                                        */
 lv_status lv_map_build_device(lv_handle h, const float* d_xyz, int64_t m);
 lv_status lv_map_add_device(lv_handle h, const float* d_xyz, int64_t n, int downsample);
+/* main.cpp:99-105 on the device: `map.add(Xt2 * Xt2.I_Rt_L() * ds_compensated, t2, true)`.  The sweep is given in the
+ * LiDAR frame (device memory) and is transformed by the filter's current state, i.e. the result of the lv_correct /
+ * lv_correct_device that precedes the call, without that state ever visiting the host.  lv_map_add_last_sweep reuses
+ * the sweep of that update (it is still resident), so one tick is lv_correct(...); lv_map_add_last_sweep(h, 1).
+ * On an empty map both build it un-downsampled (Mapper.cpp:26).  Asynchronous.                                  */
+lv_status lv_map_add_sweep_device(lv_handle h, const float* d_xyz_lidar, int64_t n, int downsample);
+lv_status lv_map_add_last_sweep(lv_handle h, int downsample);
 
 /* ---- operator boundary: the measurement model IKFoM calls (esekfom.hpp:128,1637) --------- */
 /* compat mode: fills h_x (Nm x 12, COLUMN-major like Eigen::MatrixXd) and h (Nm) exactly as

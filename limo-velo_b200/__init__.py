@@ -93,6 +93,8 @@ def lib():
     L.lv_map_build_device.argtypes = [vp, vp, i64]
     L.lv_map_add_device.argtypes = [vp, vp, i64, C.c_int]
     L.lv_map_status.argtypes = [vp]
+    L.lv_map_add_sweep_device.argtypes = [vp, vp, i64, C.c_int]
+    L.lv_map_add_last_sweep.argtypes = [vp, C.c_int]
     L.lv_measure.argtypes = [vp, dp, fp, i64, dp, dp, C.POINTER(i64)]
     L.lv_measure_reduced.argtypes = [vp, dp, fp, i64, dp, dp, C.POINTER(i64)]
     L.lv_match_all.argtypes = [vp, dp, fp, i64, C.POINTER(C.c_uint8), i32p, fp, fp, fp, fp]
@@ -344,6 +346,13 @@ class Localizer:
     def map_add_device(self, d_xyz, n, downsample=True):
         """Mapper::add from a device buffer; asynchronous (no host round trip)"""
         return _check(self.L.lv_map_add_device(self.h, C.c_void_p(d_xyz), int(n), int(downsample)))
+
+    def map_add_sweep_device(self, d_xyz_lidar, n, downsample=True):
+        """main.cpp:99-105 on the device: the LiDAR-frame sweep, transformed by the filter's current state, joins the map"""
+        return _check(self.L.lv_map_add_sweep_device(self.h, C.c_void_p(d_xyz_lidar), int(n), int(downsample)))
+
+    def map_add_last_sweep(self, downsample=True):
+        return _check(self.L.lv_map_add_last_sweep(self.h, int(downsample)))
 
     def map_status(self):
         """synchronises; raises on LV_ERR_CAPACITY (device map out of table / arena space)"""

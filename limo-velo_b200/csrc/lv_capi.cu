@@ -54,11 +54,19 @@ struct lv_context {
     UpdateCtrl* d_ctrl = nullptr;
     UpdateCtrl* h_ctrl = nullptr;      /* pinned mirror for the D2H of results */
     double* d_partials = nullptr;
+    double* d_group_rows = nullptr;    /* partials pre-reduced in groups of kPartialGroup rows (fit kernel) */
+    uint32_t* d_group_tickets = nullptr;
     int4* d_nn_a = nullptr;            /* max_points: K1 -> K2 hand-over */
     int2* d_nn_b = nullptr;
     uint32_t* d_hard_list = nullptr;   /* kHardBuckets segments of hard_segment(max_points) entries, then kCounters counters */
     float4* d_ref = nullptr;           /* max_points: reuse reference (lv_reuse_kernel) */
     uint32_t* d_redo = nullptr;        /* max_points */
+    uint32_t *d_bin_key = nullptr, *d_bin_val = nullptr, *d_bin_key_in = nullptr, *d_bin_val_in = nullptr;   /* sort_queries */
+    uint8_t* d_redo_flag = nullptr;
+    void* d_bin_tmp = nullptr;
+    size_t bin_tmp_bytes = 0;
+    int64_t last_sweep_n = 0;          /* points of the sweep d_sweep holds (lv_correct / lv_measure*), for lv_map_add_last_sweep */
+    const float* last_sweep = nullptr; /* device pointer of the sweep of the last update */
     bool use_reuse = true;
     bool use_pdl = true;               /* programmatic dependent launch between the kernels of an update */
     /* Compensator (deskew) staging: lazily allocated */
@@ -102,13 +110,10 @@ struct lv_context {
         cudaGraph_t graph;
         cudaGraphExec_t exec;
         cudaGraphNode_t begin_node;
-        std::vector<cudaGraphNode_t> measure_nodes[kMeasureKernels];   /* they carry the map view */
-        uint64_t map_version;
     };
     std::vector<UpdateGraph> graphs;
     MeasureJob* d_job = nullptr;
     bool use_graph = true;
-    uint64_t map_version = 0;          /* bumped by every rebuild: captured map views go stale */
 };
 
 static lv_status drain_events(lv_context* h) {
@@ -177,11 +182,20 @@ static MeasureArgs make_measure_args(lv_context* h, const float* d_xyz, int64_t 
     a.planes_threshold = h->prm.PLANES_THRESHOLD;
     a.estimate_extrinsics = h->prm.estimate_extrinsics;
     a.partials = h->d_partials;
+    a.group_rows = h->d_group_rows;
+    a.group_tickets = h->d_group_tickets;
     a.nn_a = h->d_nn_a;
     a.nn_b = h->d_nn_b;
     a.hard_list = h->d_hard_list;
     a.hard_seg = hard_segment(h->prm.max_points);
     a.hard_count = h->d_hard_list + (size_t)kHardBuckets * a.hard_seg;
+    if (h->prm.sort_queries) {
+        a.bin_key = h->d_bin_key; a.bin_val = h->d_bin_val; a.bin_key_in = h->d_bin_key_in; a.bin_val_in = h->d_bin_val_in;
+        a.redo_flag = h->d_redo_flag;
+        a.sort_tmp = h->d_bin_tmp; a.sort_tmp_bytes = h->bin_tmp_bytes;
+        a.sort_bits = 0;
+        for (uint32_t sl = h->map.slots; sl > 1; sl >>= 1) a.sort_bits++;
+    }
     return a;
 }
 
@@ -251,6 +265,15 @@ lv_status lv_create(const lv_params* p, lv_handle* out) {
     LV_CREATE_CUDA(cudaMalloc(&h->d_hard_list, sizeof(uint32_t) * ((size_t)kHardBuckets * hard_segment(p->max_points) + kCounters)));
     LV_CREATE_CUDA(cudaMalloc(&h->d_ref, sizeof(float4) * p->max_points));
     LV_CREATE_CUDA(cudaMalloc(&h->d_redo, sizeof(uint32_t) * (p->max_points + 64)));   /* + one block of slack: read speculatively */
+    if (p->sort_queries) {
+        LV_CREATE_CUDA(cudaMalloc(&h->d_bin_key, sizeof(uint32_t) * p->max_points));
+        LV_CREATE_CUDA(cudaMalloc(&h->d_bin_val, sizeof(uint32_t) * p->max_points));
+        LV_CREATE_CUDA(cudaMalloc(&h->d_bin_key_in, sizeof(uint32_t) * p->max_points));
+        LV_CREATE_CUDA(cudaMalloc(&h->d_bin_val_in, sizeof(uint32_t) * p->max_points));
+        LV_CREATE_CUDA(cudaMalloc(&h->d_redo_flag, p->max_points));
+        h->bin_tmp_bytes = bin_sort_tmp_bytes(p->max_points);
+        LV_CREATE_CUDA(cudaMalloc(&h->d_bin_tmp, h->bin_tmp_bytes));
+    }
     h->use_reuse = getenv("LV_NO_REUSE") == nullptr;
     h->use_pdl = getenv("LV_NO_PDL") == nullptr;
     LV_CREATE_CUDA(cudaMalloc(&h->d_job, sizeof(MeasureJob)));
@@ -260,6 +283,9 @@ lv_status lv_create(const lv_params* p, lv_handle* out) {
     LV_CREATE_CUDA(cudaMemset(h->d_ctrl, 0, sizeof(UpdateCtrl)));
     LV_CREATE_CUDA(cudaMallocHost(&h->h_ctrl, sizeof(UpdateCtrl)));
     LV_CREATE_CUDA(cudaMalloc(&h->d_partials, sizeof(double) * kPartialStride * (148 * 4 + 8)));
+    LV_CREATE_CUDA(cudaMalloc(&h->d_group_rows, sizeof(double) * kPartialStride * 32));
+    LV_CREATE_CUDA(cudaMalloc(&h->d_group_tickets, sizeof(uint32_t) * 32));
+    LV_CREATE_CUDA(cudaMemset(h->d_group_tickets, 0, sizeof(uint32_t) * 32));
     LV_CREATE_CUDA(cudaMalloc(&h->d_reduced, sizeof(double) * 160));
     LV_CREATE_CUDA(cudaMallocHost(&h->h_reduced, sizeof(double) * 160));
     LV_CREATE_CUDA(cudaMallocHost(&h->h_nevals, sizeof(int32_t) * kNevalsRing));
@@ -280,10 +306,11 @@ void lv_destroy(lv_handle h) {
     for (auto& e : h->pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& u : h->graphs) { cudaGraphExecDestroy(u.exec); cudaGraphDestroy(u.graph); }
     cudaFree(h->d_job); cudaFree(h->d_ref); cudaFree(h->d_redo);
+    cudaFree(h->d_bin_key); cudaFree(h->d_bin_val); cudaFree(h->d_bin_key_in); cudaFree(h->d_bin_val_in); cudaFree(h->d_redo_flag); cudaFree(h->d_bin_tmp);
     cudaFree(h->d_path); cudaFreeHost(h->h_path); cudaFree(h->d_times); cudaFree(h->d_deskew_in); cudaFree(h->d_bad); cudaFreeHost(h->h_bad);
     ds_free(h->ds); cudaFree(h->d_ds_in); cudaFree(h->d_ds_out);
     map_free(h->map);
-    cudaFree(h->d_sweep); cudaFree(h->d_nn_a); cudaFree(h->d_nn_b); cudaFree(h->d_hard_list); cudaFree(h->d_ctrl); cudaFreeHost(h->h_ctrl); cudaFree(h->d_partials);
+    cudaFree(h->d_sweep); cudaFree(h->d_nn_a); cudaFree(h->d_nn_b); cudaFree(h->d_hard_list); cudaFree(h->d_ctrl); cudaFreeHost(h->h_ctrl); cudaFree(h->d_partials); cudaFree(h->d_group_rows); cudaFree(h->d_group_tickets);
     cudaFree(h->d_reduced); cudaFreeHost(h->h_reduced); cudaFreeHost(h->h_nevals); cudaFree(h->d_flush);
     cudaFree(h->d_valid); cudaFree(h->d_nn_idx); cudaFree(h->d_nn_sqd); cudaFree(h->d_plane);
     cudaFree(h->d_dist); cudaFree(h->d_gworld); cudaFree(h->d_rows);
@@ -381,6 +408,36 @@ lv_status lv_map_add_device(lv_handle h, const float* d_xyz, int64_t n, int down
     return map_add_device_impl(h, d_xyz, n, downsample);
 }
 
+/* ---- the tick on the device: main.cpp:99-105 ------------------------------------------------- */
+static lv_status upload_state(lv_context* h, const double* x, const double* P);
+static lv_status add_sweep_impl(lv_context* h, const float* d_xyz_lidar, int64_t n, int downsample) {
+    if (h->state_dirty) {                                         /* the transform uses the device copy of the state */
+        lv_status s = upload_state(h, h->x, h->P);
+        if (s != LV_OK) return s;
+        h->state_dirty = false;
+    }
+    EventPair ep;
+    const bool pr = prof_begin(h, 2, &ep);
+    int launches = 0;
+    LV_CUDA(map_add_sweep(h->map, h->d_ctrl, d_xyz_lidar, n, downsample ? 1 : 0, h->stream, &launches));
+    if (pr) prof_end(h, &ep);
+    count_map_launches(h, launches);
+    return LV_OK;
+}
+lv_status lv_map_add_sweep_device(lv_handle h, const float* d_xyz_lidar, int64_t n, int downsample) {
+    if (!h || (!d_xyz_lidar && n > 0)) return LV_ERR_ARG;
+    if (n <= 0) return LV_OK;
+    if (n > h->map.add_cap) { set_error("more points than one lv_map_add can take (max_map_points)"); return LV_ERR_CAPACITY; }
+    LV_CUDA(cudaSetDevice(h->prm.device));
+    return add_sweep_impl(h, d_xyz_lidar, n, downsample);
+}
+lv_status lv_map_add_last_sweep(lv_handle h, int downsample) {
+    if (!h) return LV_ERR_ARG;
+    if (!h->last_sweep || h->last_sweep_n <= 0) { set_error("no sweep has been corrected yet"); return LV_ERR_ARG; }
+    LV_CUDA(cudaSetDevice(h->prm.device));
+    return add_sweep_impl(h, h->last_sweep, h->last_sweep_n, downsample);
+}
+
 /* ---- state ----------------------------------------------------------------------------------- */
 static lv_status fetch_results(lv_context* h);
 static lv_status sync_mirror(lv_context* h) {   /* bring the host mirror up to date after lv_correct_device */
@@ -474,13 +531,9 @@ static lv_status build_update_graph(lv_context* h, int64_t cap, lv_context::Upda
     }
     out->cap = cap;
     out->graph = graph;                 /* kept: the node handles below belong to it */
-    out->map_version = h->map_version;
     LV_CUDA(cudaGraphInstantiate(&out->exec, graph, 0));
-    /* nodes patched per launch: the begin kernel (sweep pointer and size) and, after a map update, the
-     * measurement kernels (their arguments embed the map view) */
-    MeasureArgs a = update_measure_args(h, nullptr, cap, true);
-    MeasureKernelShape shape[kMeasureKernels];
-    measure_kernel_shapes(a, measure_grid((int)cap), shape);
+    /* the one node patched per launch is the begin kernel (sweep pointer and size); the measurement kernels' arguments
+     * embed the map view, which never changes over the life of a handle (tables and arena are allocated once) */
     size_t n_nodes = 0;
     LV_CUDA(cudaGraphGetNodes(graph, nullptr, &n_nodes));
     std::vector<cudaGraphNode_t> nodes(n_nodes);
@@ -493,15 +546,8 @@ static lv_status build_update_graph(lv_context* h, int64_t cap, lv_context::Upda
         cudaKernelNodeParams kp;
         LV_CUDA(cudaGraphKernelNodeGetParams(nd, &kp));
         if (kp.func == ieskf_begin_kernel_ptr()) out->begin_node = nd;
-        for (int k = 0; k < kMeasureKernels; ++k)
-            if (kp.func == shape[k].func) out->measure_nodes[k].push_back(nd);
     }
-    const size_t evals = (size_t)h->prm.MAX_NUM_ITERS + 1;
-    if (!out->begin_node || out->measure_nodes[0].size() + out->measure_nodes[3].size() != evals ||
-        out->measure_nodes[1].size() != evals || out->measure_nodes[2].size() != evals) {
-        set_error("update graph: unexpected node set");
-        return LV_ERR_CUDA;
-    }
+    if (!out->begin_node) { set_error("update graph: begin node not found"); return LV_ERR_CUDA; }
     return LV_OK;
 }
 
@@ -535,23 +581,8 @@ static lv_status enqueue_update(lv_context* h, const float* d_xyz, int64_t n) {
     kp.blockDim = dim3(256, 1, 1);
     kp.kernelParams = args;
     LV_CUDA(cudaGraphExecKernelNodeSetParams(g->exec, g->begin_node, &kp));
-    if (g->map_version != h->map_version) {
-        MeasureArgs a = update_measure_args(h, nullptr, cap, true);
-        MeasureKernelShape shape[kMeasureKernels];
-        measure_kernel_shapes(a, measure_grid((int)cap), shape);
-        void* margs[1] = {&a};
-        for (int k = 0; k < kMeasureKernels; ++k) {
-            cudaKernelNodeParams mp = {};
-            mp.func = const_cast<void*>(shape[k].func);
-            mp.gridDim = dim3(shape[k].grid, 1, 1);
-            mp.blockDim = dim3(shape[k].block, 1, 1);
-            mp.kernelParams = margs;
-            for (cudaGraphNode_t nd : g->measure_nodes[k]) LV_CUDA(cudaGraphExecKernelNodeSetParams(g->exec, nd, &mp));
-        }
-        g->map_version = h->map_version;
-    }
     LV_CUDA(cudaGraphLaunch(g->exec, h->stream));
-    h->prof.total_launches += 1 + 4 * (h->prm.MAX_NUM_ITERS + 1) + (h->use_reuse ? h->prm.MAX_NUM_ITERS : 0);
+    h->prof.total_launches += 1 + 4 * (h->prm.MAX_NUM_ITERS + 1) + (h->use_reuse ? h->prm.MAX_NUM_ITERS : 0) + (h->prm.sort_queries ? 5 : 0);
     return LV_OK;
 }
 
@@ -562,13 +593,18 @@ static lv_status enqueue_update_kernels(lv_context* h, const float* d_xyz, int64
     if (!as_job) h->prof.total_launches += 1;
     MeasureArgs a = update_measure_args(h, d_xyz, n, as_job);
     const int grid = measure_grid((int)n);
+    if (a.bin_key) {                                              /* once per update: the sweep binned by home voxel */
+        int l = 0;
+        LV_CUDA(launch_bin(a, h->stream, pdl, &l));
+        if (!as_job) h->prof.total_launches += l;
+    }
     for (int e = 0; e <= h->prm.MAX_NUM_ITERS; ++e) {            /* i = -1 .. max_iter-1, esekfom.hpp:1634 */
         EventPair ep;
         bool pr;
         LV_CUDA(launch_measure_timed(h, a, grid, as_job ? 0 : 1, e > 0, (int)(h->update_seq % kNevalsRing), e, pdl));
         pr = prof_begin(h, 1, &ep);
         ep.upd = (int)(h->update_seq % kNevalsRing); ep.slot = e;
-        LV_CUDA(launch_ieskf_step(h->d_ctrl, h->iprm, h->d_partials, grid, h->stream, pdl));
+        LV_CUDA(launch_ieskf_step(h->d_ctrl, h->iprm, h->d_group_rows, partial_groups(grid), h->stream, pdl));
         if (pr) prof_end(h, &ep);
         if (!as_job) h->prof.total_launches += 4 + ((e > 0 && h->use_reuse) ? 1 : 0);
     }
@@ -606,6 +642,7 @@ lv_status lv_correct(lv_handle h, const float* xyz, int64_t n, double time, lv_i
     LV_CUDA(cudaMemcpyAsync(h->d_sweep, xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream));
     lv_status s = enqueue_update(h, h->d_sweep, n);
     if (s != LV_OK) return s;
+    h->last_sweep = h->d_sweep; h->last_sweep_n = n;
     s = fetch_results(h);
     h->last_time_updated = time;                                  /* Localizator.cpp:26 */
     if (logs) memcpy(logs, h->logs, sizeof(lv_iter_log) * (size_t)h->n_evals);
@@ -620,6 +657,7 @@ lv_status lv_correct_device(lv_handle h, const float* d_xyz, int64_t n, double t
     if (h->map.empty) return LV_EMPTY_MAP;
     LV_CUDA(cudaSetDevice(h->prm.device));
     lv_status s = enqueue_update(h, d_xyz, n);
+    h->last_sweep = d_xyz; h->last_sweep_n = n;
     h->last_time_updated = time;
     h->pending_fetch = true;
     return s;
@@ -654,6 +692,7 @@ static lv_status run_measure_once(lv_context* h, const double* x, const float* x
         a.g_world = h->d_gworld;
     }
     const int grid = measure_grid((int)n);
+    if (a.bin_key) { int l = 0; LV_CUDA(launch_bin(a, h->stream, 0, &l)); h->prof.total_launches += l; }
     static const bool diag_events = getenv("LV_DIAG_EVENTS") != nullptr;   /* diagnosis (tools/diag_hang.sh): which kernel does not finish? */
     if (diag_events) {
         struct Ctx { cudaStream_t st; cudaEvent_t ev[6]; int n; } ctx = {h->stream, {}, 0};
@@ -661,7 +700,7 @@ static lv_status run_measure_once(lv_context* h, const double* x, const float* x
         probe.ctx = &ctx;
         probe.at = [](void* p, int) { Ctx* c = static_cast<Ctx*>(p); cudaEventCreateWithFlags(&c->ev[c->n], cudaEventDisableTiming); cudaEventRecord(c->ev[c->n], c->st); c->n++; };
         LV_CUDA(launch_measure(a, grid, h->stream, &probe, 0, 0));
-        LV_CUDA(launch_reduce_partials(h->d_partials, grid, h->d_reduced, h->stream));
+        LV_CUDA(launch_reduce_partials(h->d_group_rows, partial_groups(grid), h->d_reduced, h->stream));
         probe.at(&ctx, 9);
         const char* names[5] = {"before search", "search", "search-upper", "fit", "reduce"};
         for (int tick = 0; tick < 200; ++tick) {           /* 20 s */
@@ -675,7 +714,7 @@ static lv_status run_measure_once(lv_context* h, const double* x, const float* x
         if (cudaEventQuery(ctx.ev[ctx.n - 1]) != cudaSuccess) { set_error("diag: measurement kernels did not finish in 20 s"); _exit(3); }
     } else {
     LV_CUDA(launch_measure_timed(h, a, grid, 1, 0, -1, 0));
-    LV_CUDA(launch_reduce_partials(h->d_partials, grid, h->d_reduced, h->stream));
+    LV_CUDA(launch_reduce_partials(h->d_group_rows, partial_groups(grid), h->d_reduced, h->stream));
     }
     LV_CUDA(cudaMemcpyAsync(h->h_reduced, h->d_reduced, sizeof(double) * 157, cudaMemcpyDeviceToHost, h->stream));
     h->prof.total_launches += 5;

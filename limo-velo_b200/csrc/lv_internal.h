@@ -13,7 +13,8 @@
 
 namespace lv {
 
-enum { kMeasureThreads = 128, kPartialStride = 96, kStepThreads = 512 };
+enum { kMeasureThreads = 128, kPartialStride = 96, kStepThreads = 512, kPartialGroup = 32 };
+inline int partial_groups(int grid) { return (grid + kPartialGroup - 1) / kPartialGroup; }
 /* The search kernel appends its uncertified queries to one of 32 lists picked by block index: thousands of atomics on
  * ONE counter cost it a 9 us tail on the first evaluation of an update (tools/timeline.py). */
 enum { kHardBuckets = 32, kCounters = 4 + kHardBuckets };
@@ -42,6 +43,8 @@ struct MeasureArgs {
     float planes_threshold;
     int32_t estimate_extrinsics;
     double* partials;          /* [grid][kPartialStride]: 78 + 12 sums, count             */
+    double* group_rows;        /* [partial_groups(grid)][kPartialStride]: the partials summed in groups of kPartialGroup rows */
+    uint32_t* group_tickets;   /* [partial_groups(grid)]: blocks of the group that have finished (fit kernel)                  */
     /* optional per-point outputs (NULL on the hot path) */
     uint8_t* valid;
     int32_t* nn_idx;
@@ -58,6 +61,15 @@ struct MeasureArgs {
     /* reuse of neighbours across the evaluations of one update (NULL: off) */
     float4* ref;               /* n: world position the stored neighbours were searched from + outsider bound */
     uint32_t* redo_list;       /* n: queries whose neighbours could not be reused (Kv -> K1)  */
+    /* binned order of the sweep (lv_params.sort_queries; NULL: per-query search from global memory) */
+    const uint32_t* bin_key;   /* n: home-voxel slot at the propagated state, ascending (0xFFFFFFFF: none) */
+    const uint32_t* bin_val;   /* n: the query at that position                                            */
+    uint32_t* bin_key_in;      /* n: unsorted, written by lv_bin_kernel                                    */
+    uint32_t* bin_val_in;
+    uint8_t* redo_flag;        /* n: 1 = search again (written by lv_reuse_kernel)                         */
+    void* sort_tmp;            /* cub::DeviceRadixSort scratch for n pairs                                 */
+    size_t sort_tmp_bytes;
+    int32_t sort_bits;         /* significant bits of a slot index                                         */
 };
 
 /* device map storage (layout: lv_voxel_map.h) + scratch of one add */
@@ -91,6 +103,9 @@ void map_free(MapBuffers& b);
 cudaError_t map_clear(MapBuffers& b, cudaStream_t st, int* launches);
 /* KD_TREE::Build (downsample = 0 on an empty map) / Add_Points: n points in DEVICE memory; asynchronous, no host round trip */
 cudaError_t map_add(MapBuffers& b, const float* d_xyz, int64_t n, int downsample, cudaStream_t st, int* launches);
+/* the sweep (LiDAR frame, device) transformed by the state in d_ctrl->x, then map_add: main.cpp:99-105 without leaving the GPU */
+cudaError_t map_add_sweep(MapBuffers& b, const UpdateCtrl* d_ctrl, const float* d_xyz_lidar, int64_t n, int downsample, cudaStream_t st,
+                          int* launches);
 cudaError_t map_fetch_counters(MapBuffers& b, cudaStream_t st);
 cudaError_t map_points_sorted(MapBuffers& b, float* host_out, int64_t cap, int64_t* n_out, cudaStream_t st);
 VoxelMapView map_view(const MapBuffers& b);
@@ -103,6 +118,9 @@ struct MeasureProbe { void (*at)(void* ctx, int stage); void* ctx; };
  * over the queries it could not vouch for; the probe then sees stage 4 before the reuse kernel */
 cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st, const MeasureProbe* probe = nullptr,
                            int reuse = 0, int pdl = 0);
+/* once per update when a.bin_key is set: lv_bin_kernel + radix sort of the (slot, query) pairs */
+cudaError_t launch_bin(const MeasureArgs& a, cudaStream_t st, int pdl, int* launches);
+size_t bin_sort_tmp_bytes(int64_t max_points);
 cudaError_t launch_ieskf_begin(UpdateCtrl* c, MeasureJob* job, const float* xyz, int n, uint32_t* counters, cudaStream_t st);
 const void* ieskf_begin_kernel_ptr();
 void measure_init();                          /* constant tables; call once before any capture           */

@@ -165,6 +165,20 @@ __global__ void __launch_bounds__(256) lv_map_unpack_kernel(const float4* __rest
     xyz[3 * (size_t)i] = p.x; xyz[3 * (size_t)i + 1] = p.y; xyz[3 * (size_t)i + 2] = p.z;
 }
 
+/* main.cpp:99-105 on the device: the sweep (LiDAR frame) in world coordinates with the state the update just produced,
+ * Xt2 * Xt2.I_Rt_L() * p in fp32 (State.cpp:79-89, RotTransl.cpp:36-48) — the very transform Mapper::match applies */
+__global__ void __launch_bounds__(256) lv_sweep_to_world_kernel(const UpdateCtrl* __restrict__ c, const float* __restrict__ xyz, uint32_t n,
+                                                                 float* __restrict__ out) {
+    __shared__ Frame s_frame;
+    if (threadIdx.x == 0) make_frame(c->x, &s_frame);
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float g[3];
+    rt_apply(s_frame.lidar_to_world, xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], g);
+    out[3 * (size_t)i] = g[0]; out[3 * (size_t)i + 1] = g[1]; out[3 * (size_t)i + 2] = g[2];
+}
+
 /* ---- host side ------------------------------------------------------------------------------------------- */
 static uint32_t pow2_at_least(uint64_t v, uint32_t lo, uint32_t hi) {
     uint64_t p = lo;
@@ -261,6 +275,15 @@ cudaError_t map_add(MapBuffers& b, const float* d_xyz, int64_t n, int downsample
     b.empty = false;
     if (launches) *launches += 5 + 4;   /* + histogram and onesweep passes of the sort (approximate) */
     return cudaGetLastError();
+}
+
+cudaError_t map_add_sweep(MapBuffers& b, const UpdateCtrl* d_ctrl, const float* d_xyz_lidar, int64_t n, int downsample, cudaStream_t st,
+                          int* launches) {
+    if (n <= 0) return cudaSuccess;
+    if (n > b.add_cap) return cudaErrorInvalidValue;
+    lv_sweep_to_world_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_ctrl, d_xyz_lidar, (uint32_t)n, b.stage_xyz);
+    if (launches) *launches += 1;
+    return map_add(b, b.stage_xyz, n, b.empty ? 0 : downsample, st, launches);
 }
 
 /* device counters -> pinned mirror; the caller synchronises the stream before reading b.h_counters */

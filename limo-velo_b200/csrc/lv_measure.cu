@@ -46,6 +46,8 @@ __device__ unsigned g_lv_phase[3][16384];
 #else
 #define LV_PHASE(k, v)
 #endif
+#include <cub/device/device_radix_sort.cuh>
+
 #include "lv_internal.h"
 
 #ifdef LV_STEP_TIMING   /* tuning build only: wall-clock timeline of the kernels of an update (graph + PDL included) */
@@ -181,6 +183,210 @@ __global__ void __launch_bounds__(LV_SEARCH_THREADS) lv_search_kernel(const Meas
     LV_TL_END(2);
 }
 
+/* ---- bulk copies into shared memory (TMA engine, 1-D form) and the mbarrier they complete on ---------------- */
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+/* global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completes `bytes` of transaction on `bar` */
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+/*
+ * Kb — bin.  Once per update (the sweep does not change across its evaluations): the home voxel's slot of every
+ * query at the propagated state.  A radix sort of the (slot, query) pairs follows (launch_bin), after which the
+ * queries of one voxel sit next to each other and lv_search_staged_kernel fetches each halo bucket once per block.
+ */
+__global__ void __launch_bounds__(128) lv_bin_kernel(const MeasureArgs a) {
+    pdl_wait();
+    pdl_trigger();
+    if (a.ctrl->done) return;
+    const JobView jb = job_view(a);
+    const int i = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (i >= a.n) return;
+    if (i >= jb.n) {            /* graph replay: the sort covers the capacity a.n; the padding sorts behind every query */
+        a.bin_key_in[i] = 0xFFFFFFFFu;
+        a.bin_val_in[i] = 0xFFFFFFFFu;
+        return;
+    }
+    const Rt32& T = a.ctrl->frame.lidar_to_world;
+    float g[3];
+    rt_apply(T, jb.xyz[3 * i], jb.xyz[3 * i + 1], jb.xyz[3 * i + 2], g);
+    uint32_t key = 0xFFFFFFFFu, bs, bc;
+    const bool finite = (fabsf(g[0]) < 1e9f) && (fabsf(g[1]) < 1e9f) && (fabsf(g[2]) < 1e9f);
+    if (finite) {
+        const int slot = level0_probe(a.map, g[0], g[1], g[2], &bs, &bc);
+        if (slot >= 0) key = (uint32_t)slot;
+    }
+    a.bin_key_in[i] = key;
+    a.bin_val_in[i] = (uint32_t)i;
+}
+
+/*
+ * K1s — search, level 0, from shared memory.  One block = LV_STAGE_QUERIES consecutive queries of the binned order,
+ * i.e. a handful of voxel runs.  Per block: the run heads read their voxel's slot (one 32-byte sector: key, bucket
+ * start and count), a block scan places the buckets in shared memory, each head issues ONE bulk copy
+ * (cp.async.bulk, completing on an mbarrier) for its bucket, and after the wait every thread scans its query's
+ * bucket out of shared memory: no per-lane merge, no shuffles, one global fetch per bucket instead of one per query
+ * (a 65 536-point Velodyne sweep has ~6 queries per home voxel).  Buckets beyond the staging budget are scanned from
+ * global memory by the same loop.
+ *   Certification is relative to the voxel the query was BINNED in (at the propagated state): the bucket holds every
+ * map point of that voxel's 3x3x3 neighbourhood, so whatever lies closer to the query than the neighbourhood's
+ * boundary is exact — also when a later iterate has moved the query into a neighbouring voxel.  What cannot be
+ * certified goes to lv_search_rings_kernel, as in the per-query kernel.  Results are identical to lv_search_kernel's.
+ *   With REDO (evaluations after the first, reuse on) the queries lv_reuse_kernel vouched for are skipped.
+ */
+#define LV_STAGE_QUERIES 128
+#define LV_STAGE_PTS 2560                      /* float4 of staged buckets per block: 40 KB */
+/* one thread scans a whole bucket: p[0 .. n) are the points, ids are bstart + j */
+__device__ __forceinline__ void scan_bucket(const float4* p, uint32_t n, uint32_t bstart, const float* g, Top5& t) {
+    uint32_t j = 0;
+    for (; j + 4 <= n; j += 4) {
+        const float4 q0 = p[j], q1 = p[j + 1], q2 = p[j + 2], q3 = p[j + 3];
+        top5_insert(t, sq_dist(g[0], g[1], g[2], q0.x, q0.y, q0.z), (int)(bstart + j));
+        top5_insert(t, sq_dist(g[0], g[1], g[2], q1.x, q1.y, q1.z), (int)(bstart + j + 1));
+        top5_insert(t, sq_dist(g[0], g[1], g[2], q2.x, q2.y, q2.z), (int)(bstart + j + 2));
+        top5_insert(t, sq_dist(g[0], g[1], g[2], q3.x, q3.y, q3.z), (int)(bstart + j + 3));
+    }
+    for (; j < n; ++j) {
+        const float4 q = p[j];
+        top5_insert(t, sq_dist(g[0], g[1], g[2], q.x, q.y, q.z), (int)(bstart + j));
+    }
+}
+__device__ __noinline__ void scan_bucket_global(const float4* p, uint32_t n, uint32_t bstart, const float* g, Top5& t) {
+    for (uint32_t j = 0; j < n; ++j) {
+        const float4 q = load_point(p + j);
+        top5_insert(t, sq_dist(g[0], g[1], g[2], q.x, q.y, q.z), (int)(bstart + j));
+    }
+}
+template <bool REDO>
+__global__ void __launch_bounds__(LV_STAGE_QUERIES) lv_search_staged_kernel(const MeasureArgs a) {
+    __shared__ __align__(16) float4 s_pts[LV_STAGE_PTS];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_key[LV_STAGE_QUERIES];
+    __shared__ uint32_t s_run_start[LV_STAGE_QUERIES];    /* bucket position in the arena                         */
+    __shared__ uint32_t s_run_count[LV_STAGE_QUERIES];
+    __shared__ uint32_t s_run_off[LV_STAGE_QUERIES];      /* position in s_pts, 0xFFFFFFFF: read from the arena   */
+    __shared__ uint32_t s_run_vox[LV_STAGE_QUERIES][3];   /* biased voxel coordinates of the run's voxel          */
+    __shared__ uint32_t s_run_need[LV_STAGE_QUERIES];
+    __shared__ uint32_t s_warp_heads[LV_STAGE_QUERIES / 32], s_warp_pts[LV_STAGE_QUERIES / 32];
+    LV_TL_SCHED();
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) mbar_init(&s_bar, 1);
+    s_run_need[tid] = 0u;
+    pdl_wait();                 /* frame (step kernel), binned order (sort), redo flags (reuse kernel) */
+    pdl_trigger();
+    LV_TL_WORK(a.ctrl, 2);
+    const int done = a.ctrl->done;
+    const Rt32 T = a.ctrl->frame.lidar_to_world;
+    const JobView jb = job_view(a);
+    if (done || (int)blockIdx.x * LV_STAGE_QUERIES >= jb.n) return;
+    const int pos = (int)blockIdx.x * LV_STAGE_QUERIES + tid;
+    const bool have = pos < jb.n;
+    const uint32_t key = have ? a.bin_key[pos] : 0xFFFFFFFFu;
+    const int qi = have ? (int)a.bin_val[pos] : 0;
+    bool active = have;
+    if (REDO && have) active = a.redo_flag[qi] != 0;
+    s_key[tid] = key;
+    __syncthreads();
+    /* runs of equal keys inside the block */
+    const bool binned = key != 0xFFFFFFFFu;
+    const bool head = binned && (tid == 0 || s_key[tid - 1] != key);
+    const unsigned hb = __ballot_sync(0xffffffffu, head);
+    if (lane == 0) s_warp_heads[warp] = (uint32_t)__popc(hb);
+    __syncthreads();
+    uint32_t run = (uint32_t)__popc(hb & (0xffffffffu >> (31 - lane)));      /* heads at or before this lane */
+    for (int w = 0; w < warp; ++w) run += s_warp_heads[w];
+    run = binned ? run - 1u : 0u;                                             /* a binned query's run index */
+    uint32_t n_runs = 0;
+    for (int w = 0; w < LV_STAGE_QUERIES / 32; ++w) n_runs += s_warp_heads[w];
+    if (binned && active) s_run_need[run] = 1u;                               /* benign race: everybody writes 1 */
+    __syncthreads();
+    /* the head of a run fetches its voxel's slot */
+    uint32_t my_count = 0;
+    if (head) {
+        const uint4 e0 = load_slot(a.map.table + 2 * (size_t)key), e1 = load_slot(a.map.table + 2 * (size_t)key + 1);
+        const uint64_t vk = (uint64_t)e0.x | ((uint64_t)e0.y << 32);
+        s_run_vox[run][0] = (uint32_t)vk & 0x1FFFFFu;
+        s_run_vox[run][1] = (uint32_t)(vk >> 21) & 0x1FFFFFu;
+        s_run_vox[run][2] = (uint32_t)(vk >> 42) & 0x1FFFFFu;
+        s_run_start[run] = e1.x;
+        s_run_count[run] = e1.y;
+        my_count = s_run_need[run] ? e1.y : 0u;
+    }
+    /* block-wide exclusive scan of the heads' counts -> staging offsets */
+    uint32_t incl = my_count;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+    }
+    if (lane == 31) s_warp_pts[warp] = incl;
+    __syncthreads();
+    uint32_t off = incl - my_count;
+    for (int w = 0; w < warp; ++w) off += s_warp_pts[w];
+    const bool staged = head && my_count > 0u && off + my_count <= (uint32_t)LV_STAGE_PTS;
+    if (head) s_run_off[run] = staged ? off : 0xFFFFFFFFu;
+    /* bytes in flight: the sum over the staged runs */
+    uint32_t my_bytes = staged ? my_count * 16u : 0u;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) my_bytes += __shfl_xor_sync(0xffffffffu, my_bytes, d);
+    __syncthreads();                              /* s_warp_pts is reused below: everybody has read it */
+    if (lane == 0) s_warp_pts[warp] = my_bytes;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t total = 0;
+        for (int w = 0; w < LV_STAGE_QUERIES / 32; ++w) total += s_warp_pts[w];
+        mbar_arrive_expect_tx(&s_bar, total);     /* the one arrival the barrier waits for + the bytes the copies bring */
+    }
+    if (staged) bulk_copy_g2s(s_pts + off, a.map.arena + s_run_start[run], my_count * 16u, &s_bar);
+    /* meanwhile: this thread's query */
+    float g[3] = {0.f, 0.f, 0.f};
+    bool finite = false;
+    if (active) {
+        rt_apply(T, jb.xyz[3 * qi], jb.xyz[3 * qi + 1], jb.xyz[3 * qi + 2], g);   /* Mapper.cpp:51 */
+        finite = (fabsf(g[0]) < 1e9f) && (fabsf(g[1]) < 1e9f) && (fabsf(g[2]) < 1e9f);
+    }
+    {   /* wait for the buckets (bounded: a lost transaction must not hang the GPU) */
+        uint32_t spins = 0;
+        while (!mbar_try_wait(&s_bar, 0u)) {
+            if (++spins > (1u << 24)) { __trap(); }
+        }
+    }
+    if (!active) return;
+    Top5 t;
+    top5_init(t, a.max_d2);
+    float cert = 0.f;
+    int st = 0;                                    /* 0 not finite, 1 bucket, 2 no bin */
+    if (finite) st = binned ? 1 : 2;
+    if (st == 1) {
+        const uint32_t bstart = s_run_start[run], n = s_run_count[run], so = s_run_off[run];
+        if (so != 0xFFFFFFFFu) scan_bucket(s_pts + so, n, bstart, g, t);          /* shared memory: LDS.128 */
+        else scan_bucket_global(a.map.arena + bstart, n, bstart, g, t);             /* did not fit the staging budget */
+        cert = neighbourhood_certified_d2(a.map.grid, s_run_vox[run][0], s_run_vox[run][1], s_run_vox[run][2], g[0], g[1], g[2]);
+    }
+    const bool settled = st == 1 && t.d4 <= cert;
+    store_neighbours(a, qi, t);
+    store_ref(a, qi, g, settled ? outsider_bound(t.d5, cert) : 0.f);
+    if (st == 2 || (st == 1 && !settled)) {
+        const uint32_t b = blockIdx.x % kHardBuckets;
+        a.hard_list[(size_t)b * a.hard_seg + atomicAdd(a.hard_count + 4 + b, 1u)] = (uint32_t)qi;
+    }
+    LV_TL_END(2);
+}
+
 /*
  * Kv — reuse.  Evaluations after the first of an update: the iterate moved by millimetres, the map not at all.
  * One thread per query re-measures its five stored neighbours from the new world position and keeps them when
@@ -231,6 +437,7 @@ __global__ void __launch_bounds__(128) lv_reuse_kernel(const MeasureArgs a) {
             redo = false;
         }
     }
+    if (have && a.redo_flag) a.redo_flag[qi] = redo ? 1 : 0;       /* the staged search walks the binned order and skips the rest */
     /* one atomic per warp */
     const unsigned m = __ballot_sync(0xffffffffu, redo);
     if (m) {
@@ -268,6 +475,7 @@ __global__ void __launch_bounds__(128) lv_search_rings_kernel(const MeasureArgs 
         if (lane >= d) incl += v;
     }
     const uint32_t n_hard = __shfl_sync(0xffffffffu, incl, 31);
+    __shared__ RingScratch s_ring[4];                  /* one per warp of the block */
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t h = warp; h < n_hard; h += n_warps) {
         int lo = 0;                                     /* first segment whose inclusive prefix exceeds h */
@@ -284,7 +492,9 @@ __global__ void __launch_bounds__(128) lv_search_rings_kernel(const MeasureArgs 
         const int2 prev = a.nn_b[qi];   /* level 0's (uncertified) 5th distance bounds the answer from above */
         Top5 u;
         float region = 0.f;
-        knn5_rings<GroupWarp>(a.map, g[0], g[1], g[2], a.max_d2, prev.x >= 0 ? __int_as_float(prev.y) : a.max_d2, u, &region);
+        __syncwarp();
+        knn5_rings_warp(a.map, g[0], g[1], g[2], a.max_d2, prev.x >= 0 ? __int_as_float(prev.y) : a.max_d2, u, &region,
+                        &s_ring[threadIdx.x >> 5]);
         if ((threadIdx.x & 31) == 0) {
             store_neighbours(a, qi, u);
             store_ref(a, qi, g, outsider_bound(u.d5, region));
@@ -378,6 +588,8 @@ __global__ void __launch_bounds__(kMeasureThreads, 4) lv_fit_kernel(const Measur
                 q[4][0] = q4.x; q[4][1] = q4.y; q[4][2] = q4.z;
                 orig[0] = __float_as_int(q0.w); orig[1] = __float_as_int(q1.w); orig[2] = __float_as_int(q2.w);
                 orig[3] = __float_as_int(q3.w); orig[4] = __float_as_int(q4.w);
+                for (int k = 0; k < 5; ++k) dsq[k] = sq_dist(g[0], g[1], g[2], q[k][0], q[k][1], q[k][2]);
+                canonical_neighbour_order(q, dsq, orig);             /* equidistant neighbours: the reference's (distance, x) order */
                 /* Plane.cpp:36-43: 5 neighbours and the farthest closer than MAX_DIST_PLANE */
                 if ((double)d4 < a.gate_d2) {
                     chosen = plane_fit(q, a.planes_threshold, abcd);               /* Plane.cpp:45-55 */
@@ -392,8 +604,6 @@ __global__ void __launch_bounds__(kMeasureThreads, 4) lv_fit_kernel(const Measur
             if (a.valid) a.valid[i] = chosen ? 1 : 0;
             if (a.g_world) { a.g_world[3 * i] = g[0]; a.g_world[3 * i + 1] = g[1]; a.g_world[3 * i + 2] = g[2]; }
             if (a.nn_idx || a.nn_sqd) {
-                if (full)
-                    for (int k = 0; k < 5; ++k) dsq[k] = sq_dist(g[0], g[1], g[2], q[k][0], q[k][1], q[k][2]);
                 for (int k = 0; k < 5; ++k) {
                     if (a.nn_idx) a.nn_idx[5 * i + k] = orig[k];
                     if (a.nn_sqd) a.nn_sqd[5 * i + k] = dsq[k];
@@ -429,6 +639,34 @@ __global__ void __launch_bounds__(kMeasureThreads, 4) lv_fit_kernel(const Measur
     double* out = a.partials + (size_t)bid * kPartialStride;
     if (tid < 90) out[tid] = acc;
     if (tid == 90) out[90] = (double)count;
+    /* Pre-reduction: the blocks form groups of kPartialGroup consecutive rows; the block of a group that finishes LAST
+     * (a ticket per group) adds the group's rows in row order into one group row.  Which block that is varies, the
+     * order of the additions does not, so the result is deterministic; the groups finish at different times and are
+     * summed on different SMs while other blocks still work, and the step kernel is left with <= 19 rows instead of 592
+     * (it used to spend a quarter of its time pulling 400 KB of partials through one SM's L2 port). */
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    const int grp = bid / kPartialGroup, r0 = grp * kPartialGroup;
+    const int r1 = r0 + kPartialGroup < n_blocks ? r0 + kPartialGroup : n_blocks;
+    if (tid == 0) {
+        const unsigned ticket = atomicAdd(a.group_tickets + grp, 1u);
+        s_last = ticket == (unsigned)(r1 - r0) - 1u ? 1 : 0;
+        if (s_last) a.group_tickets[grp] = 0u;          /* nobody else touches it before the next evaluation */
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        if (tid < 91) {
+            double v[kPartialGroup];
+#pragma unroll
+            for (int r = 0; r < kPartialGroup; ++r) v[r] = r0 + r < r1 ? __ldcg(a.partials + (size_t)(r0 + r) * kPartialStride + tid) : 0.0;
+            double sum = 0.0;
+#pragma unroll
+            for (int r = 0; r < kPartialGroup; ++r) sum += v[r];
+            a.group_rows[(size_t)grp * kPartialStride + tid] = sum;
+        }
+    }
     LV_PHASE(2, 4u);
     LV_TL_END(4);
 }
@@ -620,14 +858,17 @@ cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st, cons
     /* work-list length, a spare word, redo-list length; inside an update with pdl the kernels
      * reset them themselves (begin kernel, fit kernel) so that every node of the update is a kernel */
     if (!pdl) cudaMemsetAsync(a.hard_count, 0, kCounters * sizeof(uint32_t), st);
+    const unsigned qgrid = (unsigned)((a.n + LV_STAGE_QUERIES - 1) / LV_STAGE_QUERIES > 0 ? (a.n + LV_STAGE_QUERIES - 1) / LV_STAGE_QUERIES : 1);
     if (reuse && a.ref) {
         if (probe) probe->at(probe->ctx, 4);
         launch_k(lv_reuse_kernel, (a.n + 127) / 128 > 0 ? (a.n + 127) / 128 : 1, 128, st, pdl != 0, a);
         if (probe) probe->at(probe->ctx, 0);
-        launch_search<true>(a, group, sgrid, st, pdl != 0);
+        if (a.bin_key) launch_k(lv_search_staged_kernel<true>, qgrid, LV_STAGE_QUERIES, st, pdl != 0, a);
+        else launch_search<true>(a, group, sgrid, st, pdl != 0);
     } else {
         if (probe) probe->at(probe->ctx, 0);
-        launch_search<false>(a, group, sgrid, st, pdl != 0);
+        if (a.bin_key) launch_k(lv_search_staged_kernel<false>, qgrid, LV_STAGE_QUERIES, st, pdl != 0, a);
+        else launch_search<false>(a, group, sgrid, st, pdl != 0);
     }
     static const bool dbg_sync = getenv("LV_DEBUG_SYNC") != nullptr;   /* diagnosis: name the kernel that does not finish */
     if (dbg_sync) { cudaStreamSynchronize(st); fprintf(stderr, "[lv] search done\n"); fflush(stderr); }
@@ -640,6 +881,22 @@ cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st, cons
     if (dbg_sync) { cudaStreamSynchronize(st); fprintf(stderr, "[lv] fit done\n"); fflush(stderr); }
     if (probe) probe->at(probe->ctx, 3);
     return cudaGetLastError();
+}
+size_t bin_sort_tmp_bytes(int64_t max_points) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                    (uint32_t*)nullptr, (int)max_points, 0, 32);
+    return bytes;
+}
+cudaError_t launch_bin(const MeasureArgs& a, cudaStream_t st, int pdl, int* launches) {
+    launch_k(lv_bin_kernel, (unsigned)((a.n + 127) / 128 > 0 ? (a.n + 127) / 128 : 1), 128, st, pdl != 0, a);
+    size_t tmp = a.sort_tmp_bytes;
+    /* with a device-side job (graph replay) the sort covers the capacity a.n: positions past the sweep's n hold the
+     * previous sweep's pairs, which lv_search_staged_kernel never reads (keys are sorted per launch over [0, a.n)) */
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(a.sort_tmp, tmp, a.bin_key_in, const_cast<uint32_t*>(a.bin_key), a.bin_val_in,
+                                                    const_cast<uint32_t*>(a.bin_val), a.n, 0, a.sort_bits, st);
+    if (launches) *launches += 1 + 4;
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 cudaError_t launch_ieskf_begin(UpdateCtrl* c, MeasureJob* job, const float* xyz, int n, uint32_t* counters, cudaStream_t st) {
     lv_ieskf_begin_kernel<<<1, 256, 0, st>>>(c, job, xyz, n, counters);

@@ -172,6 +172,27 @@ LV_HD float certified_d2(const HomeGeom& h) {
     cert = cert > 0.f ? cert : 0.f;
     return cert * cert;
 }
+/* The bucket of voxel (bx, by, bz) holds every map point of the voxel's 3x3x3 neighbourhood.  For a query ANYWHERE
+ * (it may have left the voxel it was binned in), every other map point is at least as far as the neighbourhood's
+ * boundary: the squared certified radius is the squared distance to the nearest face of that 3-voxel cube, 0 outside.
+ * For a query inside the centre voxel this equals certified_d2(home_geom()). */
+LV_HD float neighbourhood_certified_d2(const MapGrid& grid, uint32_t bx, uint32_t by, uint32_t bz, float gx, float gy, float gz) {
+    const uint32_t b[3] = {bx, by, bz};
+    const float g[3] = {gx, gy, gz};
+    const float c = grid.cell0;
+    float gap = INFINITY;
+    for (int a = 0; a < 3; ++a) {
+        const float o = voxel_low(grid, b[a]);
+        const float lo = (g[a] - o) + c, hi = (c - (g[a] - o)) + c;      /* to the low / high face of the 3-voxel cube */
+        gap = gap < lo ? gap : lo;
+        gap = gap < hi ? gap : hi;
+    }
+    float amax = fabsf(gx) > fabsf(gy) ? fabsf(gx) : fabsf(gy);
+    amax = amax > fabsf(gz) ? amax : fabsf(gz);
+    float cert = gap - 2e-6f * (amax + 4.0f);
+    cert = cert > 0.f ? cert : 0.f;
+    return cert * cert;
+}
 /* squared distance from the query to the voxel at offset (dx, dy, dz) from its home voxel, rounded down */
 LV_HD float voxel_box_d2(const HomeGeom& h, int dx, int dy, int dz) {
     const int d[3] = {dx, dy, dz};
@@ -272,80 +293,7 @@ LV_HD void knn5_rings(const VoxelMapView& m, float gx, float gy, float gz, float
     const int hx = (int)bx0, hy = (int)by0, hz = (int)bz0;
     Top5 loc;
     top5_init(loc, bound);
-#if defined(__CUDA_ARCH__)
-    if (Grp::size == 32) {
-        const int lane = Grp::lane();
-        const int x0 = (hx - r < 0 ? 0 : hx - r) >> 2, x1 = (hx + r > 0x1FFFFF ? 0x1FFFFF : hx + r) >> 2;
-        const int y0 = (hy - r < 0 ? 0 : hy - r) >> 2, y1 = (hy + r > 0x1FFFFF ? 0x1FFFFF : hy + r) >> 2;
-        const int z0 = (hz - r < 0 ? 0 : hz - r) >> 2, z1 = (hz + r > 0x1FFFFF ? 0x1FFFFF : hz + r) >> 2;
-        const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, nz = z1 - z0 + 1;
-        const int nb = nx * ny * nz;
-        for (int b0 = 0; b0 < nb; b0 += 32) {
-            const int bi = b0 + lane;
-            uint64_t mask = 0ull;
-            if (bi < nb) mask = block_find(m, voxel_key((uint32_t)(x0 + bi % nx), (uint32_t)(y0 + (bi / nx) % ny), (uint32_t)(z0 + bi / (nx * ny))));
-            unsigned any = __ballot_sync(0xffffffffu, mask != 0ull);
-            while (any) {
-                const int src = __ffs(any) - 1;
-                any &= any - 1u;
-                const uint32_t mlo = __shfl_sync(0xffffffffu, (uint32_t)mask, src), mhi = __shfl_sync(0xffffffffu, (uint32_t)(mask >> 32), src);
-                const int bj = b0 + src;
-                const int cbx = (x0 + bj % nx) * 4, cby = (y0 + (bj / nx) % ny) * 4, cbz = (z0 + bj / (nx * ny)) * 4;
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const uint32_t hm = half ? mhi : mlo;
-                    uint32_t s = 0, cnt = 0;
-                    if ((hm >> lane) & 1u) {
-                        const int c = half * 32 + lane;
-                        const int vx = cbx + (c & 3), vy = cby + ((c >> 2) & 3), vz = cbz + (c >> 4);
-                        const int dx = vx - hx, dy = vy - hy, dz = vz - hz;
-                        const int ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy, az = dz < 0 ? -dz : dz;
-                        if (ax <= r && ay <= r && az <= r && voxel_box_d2(h, dx, dy, dz) < bound) {
-                            const int slot = voxel_find(m, voxel_key((uint32_t)vx, (uint32_t)vy, (uint32_t)vz));
-                            if (slot >= 0) { const uint4 e = load_slot(m.table + 2 * (size_t)slot); s = e.z; cnt = e.w; }
-                        }
-                    }
-                    if (__ballot_sync(0xffffffffu, cnt != 0u) == 0u) continue;
-                    uint32_t incl = cnt;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-                        if (lane >= d) incl += v;
-                    }
-                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-                    const uint32_t excl = incl - cnt;
-                    for (uint32_t j0 = 0; j0 < total; j0 += 128) {           /* four independent loads in flight per lane */
-                        uint32_t idx[4];
-                        bool ok[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const uint32_t j = j0 + 32u * (uint32_t)u + (uint32_t)lane;
-                            ok[u] = j < total;
-                            int lo = 0;                                      /* first voxel whose inclusive prefix exceeds j */
-#pragma unroll
-                            for (int step = 16; step > 0; step >>= 1) {
-                                const uint32_t v = __shfl_sync(0xffffffffu, incl, lo + step - 1);
-                                if (v <= j) lo += step;
-                            }
-                            lo = lo > 31 ? 31 : lo;
-                            const uint32_t sv = __shfl_sync(0xffffffffu, s, lo), ev = __shfl_sync(0xffffffffu, excl, lo);
-                            idx[u] = sv + (j - ev);
-                        }
-                        float4 q[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) q[u] = ok[u] ? load_point(m.arena + idx[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (ok[u]) top5_insert(loc, sq_dist(gx, gy, gz, q[u].x, q[u].y, q[u].z), (int)idx[u]);
-                    }
-                }
-            }
-        }
-        Grp::merge(loc, bound, out);
-        return;
-    }
-#endif
-    for (int dz = -r; dz <= r; ++dz)          /* single-lane form of the same search */
+    for (int dz = -r; dz <= r; ++dz)          /* single-lane form (host shim); the device runs knn5_rings_warp below */
         for (int dy = -r; dy <= r; ++dy)
             for (int dx = -r; dx <= r; ++dx) {
                 const int cx = hx + dx, cy = hy + dy, cz = hz + dz;
@@ -358,6 +306,215 @@ LV_HD void knn5_rings(const VoxelMapView& m, float gx, float gy, float gz, float
                 scan_run(m.arena + e.z, e.w, (int)e.z, gx, gy, gz, loc);
             }
     Grp::merge(loc, bound, out);
+}
+
+#if defined(__CUDACC__)
+/*
+ * knn5_rings for one WARP (same voxel set, same result as the single-lane form above), arranged so that a query costs a
+ * handful of dependent memory round trips:
+ *   1. the occupancy masks of all blocks overlapping the voxel range (<= 128: four per lane, kept in registers)
+ *   2. every lane walks the SET bits of its masks (work proportional to the occupied voxels, not to the volume of the
+ *      range), keeps the voxels of the wanted rings whose box lies inside the bound, and the warp compacts them into a
+ *      candidate list in shared memory (count, scan, write: deterministic order)
+ *   3. the candidates, 32 at a time: one slot probe per lane, a warp scan of the counts flattens their own points into
+ *      one index range, the lanes stride over it with four independent loads in flight
+ * A query that knows nothing yet (no bucket at level 0: bound0 = the search radius) first looks at rings <= 3 only;
+ * what it finds there usually shrinks the bound so much that the outer rings are pruned by their box distance.
+ */
+enum { kRingBlocksPerLane = 4, kRingCands = 1024 };
+struct RingScratch {
+    uint32_t cand[kRingCands];            /* (dx + 64) | (dy + 64) << 8 | (dz + 64) << 16 */
+};
+__device__ __forceinline__ void rings_process_candidates(const VoxelMapView& m, const RingScratch* sm, uint32_t n_cand, int hx, int hy, int hz,
+                                                         float gx, float gy, float gz, Top5& loc) {
+    const int lane = (int)(threadIdx.x & 31u);
+    for (uint32_t c0 = 0; c0 < n_cand; c0 += 32) {
+        uint32_t s = 0, cnt = 0;
+        if (c0 + (uint32_t)lane < n_cand) {
+            const uint32_t pk = sm->cand[c0 + lane];
+            const int vx = hx + (int)(pk & 0xFFu) - 64, vy = hy + (int)((pk >> 8) & 0xFFu) - 64, vz = hz + (int)((pk >> 16) & 0xFFu) - 64;
+            const int slot = voxel_find(m, voxel_key((uint32_t)vx, (uint32_t)vy, (uint32_t)vz));
+            if (slot >= 0) { const uint4 e = load_slot(m.table + 2 * (size_t)slot); s = e.z; cnt = e.w; }
+        }
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t excl = incl - cnt;
+        for (uint32_t j0 = 0; j0 < total; j0 += 128) {           /* four independent loads in flight per lane */
+            uint32_t idx[4];
+            bool ok[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t j = j0 + 32u * (uint32_t)u + (uint32_t)lane;
+                ok[u] = j < total;
+                int lo = 0;                                      /* first voxel whose inclusive prefix exceeds j */
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const uint32_t v = __shfl_sync(0xffffffffu, incl, lo + step - 1);
+                    if (v <= j) lo += step;
+                }
+                lo = lo > 31 ? 31 : lo;
+                const uint32_t sv = __shfl_sync(0xffffffffu, s, lo), ev = __shfl_sync(0xffffffffu, excl, lo);
+                idx[u] = sv + (j - ev);
+            }
+            float4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q[u] = ok[u] ? load_point(m.arena + idx[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (ok[u]) top5_insert(loc, sq_dist(gx, gy, gz, q[u].x, q[u].y, q[u].z), (int)idx[u]);
+        }
+    }
+}
+__device__ __forceinline__ void broadcast_top5(Top5& t, int src) {
+    t.d0 = __shfl_sync(0xffffffffu, t.d0, src); t.d1 = __shfl_sync(0xffffffffu, t.d1, src); t.d2 = __shfl_sync(0xffffffffu, t.d2, src);
+    t.d3 = __shfl_sync(0xffffffffu, t.d3, src); t.d4 = __shfl_sync(0xffffffffu, t.d4, src); t.d5 = __shfl_sync(0xffffffffu, t.d5, src);
+    t.i0 = __shfl_sync(0xffffffffu, t.i0, src); t.i1 = __shfl_sync(0xffffffffu, t.i1, src); t.i2 = __shfl_sync(0xffffffffu, t.i2, src);
+    t.i3 = __shfl_sync(0xffffffffu, t.i3, src); t.i4 = __shfl_sync(0xffffffffu, t.i4, src);
+}
+__device__ __forceinline__ void knn5_rings_warp(const VoxelMapView& m, float gx, float gy, float gz, float max_d2, float bound0, Top5& out,
+                                                float* region_d2, RingScratch* sm) {
+    const uint32_t bx0 = voxel_coord(m.grid, gx), by0 = voxel_coord(m.grid, gy), bz0 = voxel_coord(m.grid, gz);
+    const HomeGeom h = home_geom(m.grid, bx0, by0, bz0, gx, gy, gz);
+    float bound = nextafterf(bound0, INFINITY);
+    {
+        const float wide = bound0 * 1.21f;
+        bound = bound > wide ? bound : wide;
+    }
+    bound = bound < max_d2 ? bound : max_d2;
+    int r = (int)ceilf(fsqrt(bound) / h.edge * 1.0001f);
+    r = r < 1 ? 1 : (r > 63 ? 63 : r);
+    const int hx = (int)bx0, hy = (int)by0, hz = (int)bz0;
+    const int lane = (int)(threadIdx.x & 31u);
+    const int vx0 = hx - r < 0 ? 0 : hx - r, vx1 = hx + r > 0x1FFFFF ? 0x1FFFFF : hx + r;
+    const int vy0 = hy - r < 0 ? 0 : hy - r, vy1 = hy + r > 0x1FFFFF ? 0x1FFFFF : hy + r;
+    const int vz0 = hz - r < 0 ? 0 : hz - r, vz1 = hz + r > 0x1FFFFF ? 0x1FFFFF : hz + r;
+    const int x0 = vx0 >> 2, y0 = vy0 >> 2, z0 = vz0 >> 2;
+    const int nx = (vx1 >> 2) - x0 + 1, ny = (vy1 >> 2) - y0 + 1, nz = (vz1 >> 2) - z0 + 1;
+    const int nb = nx * ny * nz;
+    if (nb > 32 * kRingBlocksPerLane) {               /* a range no 2 m search produces: the single-lane form, on lane 0 */
+        Top5 t1;
+        top5_init(t1, bound);
+        float reg = bound;
+        if (lane == 0) knn5_rings<GroupSerial>(m, gx, gy, gz, max_d2, bound0, t1, &reg);
+        broadcast_top5(t1, 0);
+        out = t1;
+        if (region_d2) *region_d2 = __shfl_sync(0xffffffffu, reg, 0);
+        return;
+    }
+    /* 1. block masks */
+    unsigned long long mk[kRingBlocksPerLane];
+#pragma unroll
+    for (int u = 0; u < kRingBlocksPerLane; ++u) {
+        const int bi = lane + 32 * u;
+        mk[u] = bi < nb ? block_find(m, voxel_key((uint32_t)(x0 + bi % nx), (uint32_t)(y0 + (bi / nx) % ny), (uint32_t)(z0 + bi / (nx * ny)))) : 0ull;
+    }
+    Top5 loc;
+    top5_init(loc, bound);
+    /* passes over ring intervals [rlo, rhi]: one pass when level 0 left a bound, rings <= 3 first when it did not */
+    const bool blind = !(bound0 < max_d2);
+    int rlo = 0, rhi = (blind && r > 3) ? 3 : r;
+    for (;;) {
+        /* 2. candidates of this pass: count, scan, write */
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+            uint32_t at = 0;
+            if (pass == 1) {
+                uint32_t incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                at = incl - cnt;
+                cnt = __shfl_sync(0xffffffffu, incl, 31);            /* from here on: the warp's total */
+            }
+#pragma unroll
+            for (int u = 0; u < kRingBlocksPerLane; ++u) {
+                unsigned long long mm = mk[u];
+                const int bi = lane + 32 * u;
+                const int cbx = (x0 + bi % nx) * 4, cby = (y0 + (bi / nx) % ny) * 4, cbz = (z0 + bi / (nx * ny)) * 4;
+                while (mm) {
+                    const int c = __ffsll((long long)mm) - 1;
+                    mm &= mm - 1ull;
+                    const int dx = cbx + (c & 3) - hx, dy = cby + ((c >> 2) & 3) - hy, dz = cbz + (c >> 4) - hz;
+                    const int ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy, az = dz < 0 ? -dz : dz;
+                    const int cheb = ax > ay ? (ax > az ? ax : az) : (ay > az ? ay : az);
+                    if (cheb < rlo || cheb > rhi || !(voxel_box_d2(h, dx, dy, dz) < bound)) continue;
+                    if (pass == 0) ++cnt;
+                    else { if (at < (uint32_t)kRingCands) sm->cand[at] = (uint32_t)(dx + 64) | ((uint32_t)(dy + 64) << 8) | ((uint32_t)(dz + 64) << 16); ++at; }
+                }
+            }
+        }
+        __syncwarp();
+        if (cnt > (uint32_t)kRingCands) {            /* more occupied voxels in range than the list holds (volumetric map, tiny voxels) */
+            Top5 t1;
+            top5_init(t1, bound);
+            float reg = bound;
+            if (lane == 0) knn5_rings<GroupSerial>(m, gx, gy, gz, max_d2, bound0, t1, &reg);
+            broadcast_top5(t1, 0);
+            out = t1;
+            if (region_d2) *region_d2 = __shfl_sync(0xffffffffu, reg, 0);
+            return;
+        }
+        /* 3. probe + scan */
+        rings_process_candidates(m, sm, cnt, hx, hy, hz, gx, gy, gz, loc);
+        __syncwarp();
+        if (rhi >= r) break;
+        /* blind query, inner rings done: what was found bounds the rest */
+        Top5 t;
+        GroupWarp::merge(loc, bound, t);
+        float gap = h.lo[0] < h.hi[0] ? h.lo[0] : h.hi[0];
+        gap = gap < h.lo[1] ? gap : h.lo[1]; gap = gap < h.hi[1] ? gap : h.hi[1];
+        gap = gap < h.lo[2] ? gap : h.lo[2]; gap = gap < h.hi[2] ? gap : h.hi[2];
+        float seen = (float)rhi * h.edge + gap - h.slack * (float)(rhi + 1);      /* everything closer than this has been looked at */
+        seen = seen > 0.f ? seen : 0.f;
+        if (t.i4 >= 0 && t.d4 <= seen * seen) {       /* five found inside the certified radius: final */
+            out = t;
+            if (region_d2) *region_d2 = seen * seen < bound ? seen * seen : bound;
+            return;
+        }
+        if (t.i4 >= 0) {                              /* five found: nothing beyond their 5th distance (plus the reuse margin) matters */
+            float nbnd = nextafterf(t.d4, INFINITY);
+            const float wide = t.d4 * 1.21f;
+            nbnd = nbnd > wide ? nbnd : wide;
+            bound = nbnd < bound ? nbnd : bound;
+        }
+        /* put the five back (lane 0) and go on with the outer rings */
+        top5_init(loc, bound);
+        if (lane == 0) {
+            loc = t;                                  /* placeholders (id -1) carry the bound */
+            if (loc.i0 < 0) loc.d0 = bound; if (loc.i1 < 0) loc.d1 = bound; if (loc.i2 < 0) loc.d2 = bound;
+            if (loc.i3 < 0) loc.d3 = bound; if (loc.i4 < 0) loc.d4 = bound;
+        }
+        rlo = rhi + 1;
+        rhi = r;
+    }
+    if (region_d2) *region_d2 = bound;
+    GroupWarp::merge(loc, bound, out);
+}
+#endif
+
+/*
+ * The reference orders neighbours of (nearly) equal distance by x: PointType_CMP (ikd_Tree.h:109-115) compares x when
+ * |dist - dist'| < 1e-10, so Nearest_Search's list is ascending in (distance, x).  Which of two equidistant points a
+ * search meets first depends on how it walks the map (lanes, buckets, rings); that must not leak into the plane fit,
+ * whose rounding depends on the order of its five points.  Called on the five neighbours (ascending distances) before
+ * the fit.  (Seen on the bench data: one query of 65 536 in sweep 1 has its 3rd and 4th neighbour at equal distance.)
+ */
+LV_HD void canonical_neighbour_order(float (*q)[3], float* d, int* id) {
+    for (int pass = 0; pass < 4; ++pass)
+        for (int k = 0; k < 4; ++k)
+            if (fabs((double)(d[k + 1] - d[k])) < 1e-10 && q[k + 1][0] < q[k][0]) {
+                for (int a = 0; a < 3; ++a) { const float t = q[k][a]; q[k][a] = q[k + 1][a]; q[k + 1][a] = t; }
+                const float td = d[k]; d[k] = d[k + 1]; d[k + 1] = td;
+                const int ti = id[k]; id[k] = id[k + 1]; id[k + 1] = ti;
+            }
 }
 
 /*

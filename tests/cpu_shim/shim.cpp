@@ -175,11 +175,14 @@ void shim_match_all(const ShimMap* sm, const double* x, const ShimParams* p, con
         float abcd[4] = {0, 0, 0, 0}, d = 0;
         double row[12] = {0}, h = 0;
         bool chosen = false;
-        const int ids[5] = {t.i0, t.i1, t.i2, t.i3, t.i4};
-        const float ds[5] = {t.d0, t.d1, t.d2, t.d3, t.d4};
-        if (t.i4 >= 0 && (double)t.d4 < gate) {
-            float q[5][3];
+        int ids[5] = {t.i0, t.i1, t.i2, t.i3, t.i4};
+        float ds[5] = {t.d0, t.d1, t.d2, t.d3, t.d4};
+        float q[5][3];
+        if (t.i4 >= 0) {
             for (int k = 0; k < 5; ++k) { q[k][0] = src[ids[k]].x; q[k][1] = src[ids[k]].y; q[k][2] = src[ids[k]].z; }
+            canonical_neighbour_order(q, ds, ids);
+        }
+        if (t.i4 >= 0 && (double)t.d4 < gate) {
             chosen = plane_fit(q, p->planes_threshold, abcd);
             if (chosen) {
                 d = plane_dist(abcd, g);

@@ -84,5 +84,8 @@ def test_cfg3_ouster_10m_map(lv, O):
     loc.map_add(g, downsample=True)
     om.add(g, downsample=True)
     loc.map_status()
-    assert abs(loc.map_size() - om.size()) <= 1e-5 * om.size()
+    # (KD_TREE::size() itself over-counts at this scale — it reported 10 043 088 for a flatten() of 10 026 927 points here,
+    # lazily deleted nodes of subtrees waiting for their rebuild — so the comparison is with the flattened content)
+    ref_n = len(om.points())
+    assert abs(loc.map_size() - ref_n) <= 1e-5 * ref_n, (loc.map_size(), ref_n)
     loc.close()

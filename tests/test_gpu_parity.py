@@ -199,3 +199,36 @@ def test_map_build_roundtrip_and_add(lv, O, scene_xaloc):
     r = om.match_all(sc.x_prop, sc.oprm, sc.sweep)
     assert (g["valid"] == r["valid"]).all() and (g["plane"] == r["plane"]).all()
     loc.close()
+
+
+def test_tick_on_the_device_equals_the_host_path(lv, O, scene_xaloc):
+    """main.cpp:84-105 without leaving the GPU: lv_correct + lv_map_add_last_sweep (the sweep is transformed by the update's own
+    result on the device and merged under the 0.2 m rule) must leave exactly the map that the host path leaves
+    (read the state back, transform in fp32 like State * RotTransl * point, lv_map_add)."""
+    sc = scene_xaloc
+    om = _oracle_map(O, sc)
+    a, b = lv.Localizer(sc.prm), lv.Localizer(sc.prm)
+    for loc in (a, b):
+        loc.map_build(sc.map)
+    x = sc.x_prop.copy()
+    for k in range(2):
+        for loc in (a, b):
+            loc.set_state(x, sc.P0)
+        st, xa, Pa, _ = a.correct(sc.sweep)
+        st, xb, Pb, _ = b.correct(sc.sweep)
+        assert (xa == xb).all()
+        g = om.match_all(xa, sc.oprm, sc.sweep)["g"]              # fp32 world points of Mapper::match == main.cpp:101's
+        a.map_add(g, downsample=True)
+        b.map_add_last_sweep(downsample=True)
+        a.map_status(); b.map_status()
+        assert a.map_size() == b.map_size() > len(sc.map)
+        assert sorted(map(tuple, a.map_points().tolist())) == sorted(map(tuple, b.map_points().tolist()))
+        x = xa.copy()
+        x[0] += 0.3                                                  # the next tick starts somewhere else
+    # and the device variant with an explicit buffer
+    d = b.upload(sc.sweep)
+    b.map_add_sweep_device(d, len(sc.sweep), downsample=True)
+    a.map_add(om.match_all(b.get_state()[0], sc.oprm, sc.sweep)["g"], downsample=True)
+    assert sorted(map(tuple, a.map_points().tolist())) == sorted(map(tuple, b.map_points().tolist()))
+    b.device_free(d)
+    a.close(); b.close()
