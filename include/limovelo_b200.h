@@ -179,6 +179,10 @@ lv_status lv_get_state(lv_handle h, double* x, double* P);               /* get_
 lv_status lv_init_state(lv_handle h, const float q_imu[4]);
 /* Localizator::propagate -> esekf::predict (Localizator.cpp:159-173, esekfom.hpp:279-384)    */
 lv_status lv_predict(lv_handle h, const double acc[3], const double gyro[3], double dt);
+/* Localizator::propagate_to (Localizator.cpp:59-75) on the DEVICE: the k IMU samples between two sweeps (acc, gyro: k x 3,
+ * dt: k) run through esekf::predict in one launch; the filter state stays in HBM, so update -> propagate -> update needs no
+ * host round trip (lv_get_state fetches it when the caller wants to publish it).  Same arithmetic as lv_predict.        */
+lv_status lv_propagate_device(lv_handle h, const double* acc, const double* gyro, const double* dt, int32_t k);
 /* the same two host-side steps on caller-owned (x, P), no handle and no GPU involved           */
 lv_status lv_init_state_host(const lv_params* p, const float q_imu[4], double* x, double* P);
 lv_status lv_predict_host(const lv_params* p, const double acc[3], const double gyro[3], double dt,
@@ -273,6 +277,51 @@ lv_status lv_pointcloud2_to_points(lv_lidar_type type, const lv_cloud_layout* la
 /* PointCloudProcessor::sort_points (PointCloudProcessor.cpp:114-123): order of the points by time (stable; the
  * reference's std::sort leaves equal stamps in unspecified order)                                          */
 lv_status lv_time_sort_indices(const double* time, int64_t n, int32_t* idx_out);
+
+/* lv_pointcloud2_to_points with the bounds pcl::fromROSMsg takes from the message: every field used lies inside point_step
+ * and n points fit data_bytes (LV_ERR_ARG otherwise)                                                                    */
+lv_status lv_pointcloud2_to_points_checked(lv_lidar_type type, const lv_cloud_layout* layout, const uint8_t* data, int64_t data_bytes,
+                                           int64_t n, uint64_t header_stamp_us, int stamp_beginning, int offset_beginning,
+                                           double full_rotation_time, float* xyz, double* time, float* intensity, float* range);
+
+/* ---- rosbag reader (format 2.0; replaces roscpp / `rosbag play` in front of Accumulator::receive_lidar / receive_imu,
+ * src/main.cpp:27-39, src/Modules/Accumulator.cpp:39-60).  Sequential read of uncompressed bags (bz2 / lz4 chunks are
+ * refused with LV_ERR_IO: `rosbag decompress` first).  Host code.                                                       */
+typedef struct lv_bag lv_bag;
+typedef struct lv_bag_message {
+    int32_t conn;              /* connection id                                                   */
+    const char* topic;         /* e.g. "/velodyne_points"; valid while the bag is open            */
+    const char* type;          /* e.g. "sensor_msgs/PointCloud2"                                  */
+    uint32_t sec, nsec;        /* receive time of the record                                      */
+    const uint8_t* data;       /* the serialised message (points into the bag's buffer)           */
+    int64_t size;
+} lv_bag_message;
+lv_status lv_bag_open(const char* path, lv_bag** out);
+void lv_bag_close(lv_bag* bag);
+void lv_bag_rewind(lv_bag* bag);
+int32_t lv_bag_connection_count(const lv_bag* bag);
+/* next message in file order: 1 = *msg filled, 0 = end of the bag, -1 = malformed */
+int lv_bag_next(lv_bag* bag, lv_bag_message* msg);
+/* sensor_msgs/PointCloud2 -> a view of the point bytes + the offsets of the fields `type`'s point struct uses
+ * (include/Headers/Common.hpp:109-221), ready for lv_pointcloud2_to_points_checked                                      */
+typedef struct lv_pointcloud2_view {
+    uint32_t stamp_sec, stamp_nsec;      /* header.stamp                                          */
+    uint32_t height, width, point_step, row_step;
+    int32_t is_bigendian, is_dense;
+    int64_t n_points;                    /* height x width                                        */
+    const uint8_t* data;
+    int64_t data_bytes;
+    lv_cloud_layout layout;
+} lv_pointcloud2_view;
+lv_status lv_bag_parse_pointcloud2(const uint8_t* msg, int64_t size, lv_lidar_type type, lv_pointcloud2_view* out);
+/* sensor_msgs/Imu (what Accumulator::receive_imu reads: IMU.cpp:18-40) */
+typedef struct lv_imu_sample {
+    uint32_t stamp_sec, stamp_nsec;
+    double orientation[4];               /* x y z w                                                */
+    double angular_velocity[3];
+    double linear_acceleration[3];
+} lv_imu_sample;
+lv_status lv_bag_parse_imu(const uint8_t* msg, int64_t size, lv_imu_sample* out);
 
 #ifdef __cplusplus
 }

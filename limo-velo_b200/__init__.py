@@ -102,6 +102,7 @@ def lib():
     L.lv_get_state.argtypes = [vp, dp, dp]
     L.lv_init_state.argtypes = [vp, fp]
     L.lv_predict.argtypes = [vp, dp, dp, C.c_double]
+    L.lv_propagate_device.argtypes = [vp, dp, dp, dp, C.c_int32]
     L.lv_init_state_host.argtypes = [C.POINTER(Params), fp, dp, dp]
     L.lv_predict_host.argtypes = [C.POINTER(Params), dp, dp, C.c_double, dp, dp]
     L.lv_correct.argtypes = [vp, fp, i64, C.c_double, C.POINTER(IterLog), i32p, dp, dp]
@@ -346,6 +347,14 @@ class Localizer:
     def map_add_device(self, d_xyz, n, downsample=True):
         """Mapper::add from a device buffer; asynchronous (no host round trip)"""
         return _check(self.L.lv_map_add_device(self.h, C.c_void_p(d_xyz), int(n), int(downsample)))
+
+    def propagate_device(self, acc, gyro, dt):
+        """Localizator::propagate_to on the device: k IMU samples (k x 3, k x 3, k), one launch, the state stays in HBM"""
+        acc = np.ascontiguousarray(acc, np.float64).reshape(-1, 3)
+        gyro = np.ascontiguousarray(gyro, np.float64).reshape(-1, 3)
+        dt = np.ascontiguousarray(dt, np.float64).reshape(-1)
+        assert len(acc) == len(gyro) == len(dt)
+        return _check(self.L.lv_propagate_device(self.h, _d(acc), _d(gyro), _d(dt), len(dt)))
 
     def map_add_sweep_device(self, d_xyz_lidar, n, downsample=True):
         """main.cpp:99-105 on the device: the LiDAR-frame sweep, transformed by the filter's current state, joins the map"""

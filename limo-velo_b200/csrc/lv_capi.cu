@@ -20,6 +20,7 @@
 #include "../../include/limovelo_b200.h"
 #include "lv_host.h"
 #include "lv_internal.h"
+#include "lv_predict.h"
 
 using namespace lv;
 
@@ -65,6 +66,8 @@ struct lv_context {
     uint8_t* d_redo_flag = nullptr;
     void* d_bin_tmp = nullptr;
     size_t bin_tmp_bytes = 0;
+    double* d_imu = nullptr;           /* kImuBatch x 7: lv_propagate_device */
+    double* h_imu = nullptr;           /* pinned */
     int64_t last_sweep_n = 0;          /* points of the sweep d_sweep holds (lv_correct / lv_measure*), for lv_map_add_last_sweep */
     const float* last_sweep = nullptr; /* device pointer of the sweep of the last update */
     bool use_reuse = true;
@@ -305,7 +308,7 @@ void lv_destroy(lv_handle h) {
     for (auto& e : h->pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : h->pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& u : h->graphs) { cudaGraphExecDestroy(u.exec); cudaGraphDestroy(u.graph); }
-    cudaFree(h->d_job); cudaFree(h->d_ref); cudaFree(h->d_redo);
+    cudaFree(h->d_job); cudaFree(h->d_ref); cudaFree(h->d_redo); cudaFree(h->d_imu); cudaFreeHost(h->h_imu);
     cudaFree(h->d_bin_key); cudaFree(h->d_bin_val); cudaFree(h->d_bin_key_in); cudaFree(h->d_bin_val_in); cudaFree(h->d_redo_flag); cudaFree(h->d_bin_tmp);
     cudaFree(h->d_path); cudaFreeHost(h->h_path); cudaFree(h->d_times); cudaFree(h->d_deskew_in); cudaFree(h->d_bad); cudaFreeHost(h->h_bad);
     ds_free(h->ds); cudaFree(h->d_ds_in); cudaFree(h->d_ds_out);
@@ -473,6 +476,37 @@ lv_status lv_predict(lv_handle h, const double acc[3], const double gyro[3], dou
     sync_mirror(h);
     lvh_predict(h->prm, acc, gyro, dt, h->x, h->P);
     h->state_dirty = true;
+    return LV_OK;
+}
+/* Localizator::propagate_to on the device (Localizator.cpp:59-75): k IMU samples, one launch, no host round trip */
+lv_status lv_propagate_device(lv_handle h, const double* acc, const double* gyro, const double* dt, int32_t k) {
+    enum { kImuBatch = 512 };
+    if (!h || !acc || !gyro || !dt || k < 0) return LV_ERR_ARG;
+    if (k == 0) return LV_OK;
+    LV_CUDA(cudaSetDevice(h->prm.device));
+    if (!h->d_imu) {
+        LV_CUDA(cudaMalloc(&h->d_imu, sizeof(double) * 7 * kImuBatch));
+        LV_CUDA(cudaMallocHost(&h->h_imu, sizeof(double) * 7 * kImuBatch));
+    }
+    if (h->state_dirty) {                                         /* the host mirror is newer (lv_set_state / lv_predict): bring it over */
+        lv_status s = upload_state(h, h->x, h->P);
+        if (s != LV_OK) return s;
+        h->state_dirty = false;
+    }
+    const PredictNoise noise = {h->prm.covariance_gyroscope, h->prm.covariance_acceleration, h->prm.covariance_bias_gyroscope,
+                                h->prm.covariance_bias_acceleration};
+    for (int32_t s0 = 0; s0 < k; s0 += kImuBatch) {
+        const int32_t kb = k - s0 < kImuBatch ? k - s0 : kImuBatch;
+        if (s0 > 0) LV_CUDA(cudaStreamSynchronize(h->stream));    /* the pinned staging buffer is reused */
+        for (int32_t i = 0; i < kb; ++i) {
+            for (int a = 0; a < 3; ++a) { h->h_imu[7 * i + a] = acc[3 * (s0 + i) + a]; h->h_imu[7 * i + 3 + a] = gyro[3 * (s0 + i) + a]; }
+            h->h_imu[7 * i + 6] = dt[s0 + i];
+        }
+        LV_CUDA(cudaMemcpyAsync(h->d_imu, h->h_imu, sizeof(double) * 7 * kb, cudaMemcpyHostToDevice, h->stream));
+        LV_CUDA(launch_predict(h->d_ctrl, noise, h->d_imu, kb, h->stream));
+        h->prof.total_launches += 1;
+    }
+    h->pending_fetch = true;                                      /* the device now holds the newest (x, P) */
     return LV_OK;
 }
 double lv_last_time_updated(lv_handle h) { return h ? h->last_time_updated : -1; }

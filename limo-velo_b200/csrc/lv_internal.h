@@ -133,6 +133,8 @@ cudaError_t launch_ieskf_step(UpdateCtrl* c, const IeskfParams& prm, const doubl
                               cudaStream_t st, int pdl = 0);
 /* stand-alone reduction of the partials (operator-boundary calls): out[0:144) HTH, [144:156) HTh, [156] Nm */
 cudaError_t launch_reduce_partials(const double* partials, int n_partials, double* out, cudaStream_t st);
+struct PredictNoise;
+cudaError_t launch_predict(UpdateCtrl* c, const PredictNoise& noise, const double* d_imu, int k, cudaStream_t st);
 cudaError_t launch_set_frame(UpdateCtrl* c, cudaStream_t st);   /* frame from c->x, done = 0 */
 cudaError_t launch_l2_flush(void* buf, size_t bytes, cudaStream_t st);
 

@@ -49,6 +49,7 @@ __device__ unsigned g_lv_phase[3][16384];
 #include <cub/device/device_radix_sort.cuh>
 
 #include "lv_internal.h"
+#include "lv_predict.h"
 
 #ifdef LV_STEP_TIMING   /* tuning build only: wall-clock timeline of the kernels of an update (graph + PDL included) */
 __device__ unsigned long long g_tl[5][8][8];   /* [scheduled | past the wait | end (thread 0) | last block past the wait | end (any warp)][evaluation][kind], ns */
@@ -779,6 +780,20 @@ __global__ void __launch_bounds__(256) lv_ieskf_begin_kernel(UpdateCtrl* c, Meas
     ieskf_begin(ex, c);
 }
 
+/* Localizator::propagate_to (Localizator.cpp:59-75): every IMU sample between two sweeps through esekf::predict, one launch,
+ * one thread block; imu = k x 7 doubles (acc, gyro, dt).  The state stays in UpdateCtrl: update -> propagate -> update needs
+ * no host round trip. */
+__global__ void __launch_bounds__(256) lv_predict_kernel(UpdateCtrl* c, const PredictNoise noise, const double* __restrict__ imu, int k) {
+    __shared__ PredictWork w;
+    ExecBlock ex;
+    LV_PAR(i, kStateLen) w.x[i] = c->x[i];
+    LV_PAR(i, kN * kN) w.P[i] = c->P[i];
+    ex.sync();
+    for (int s = 0; s < k; ++s) predict_step(ex, noise, imu + 7 * s, imu + 7 * s + 3, imu[7 * s + 6], &w);
+    LV_PAR(i, kStateLen) c->x[i] = w.x[i];
+    LV_PAR(i, kN * kN) c->P[i] = w.P[i];
+}
+
 __global__ void lv_set_frame_kernel(UpdateCtrl* c) {
     if (threadIdx.x == 0) {
         make_frame(c->x, &c->frame);
@@ -912,6 +927,10 @@ cudaError_t launch_ieskf_step(UpdateCtrl* c, const IeskfParams& prm, const doubl
 cudaError_t launch_reduce_partials(const double* partials, int n_partials, double* out, cudaStream_t st) {
     init_pairs();
     lv_reduce_partials_kernel<<<1, kStepThreads, 0, st>>>(partials, n_partials, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_predict(UpdateCtrl* c, const PredictNoise& noise, const double* d_imu, int k, cudaStream_t st) {
+    lv_predict_kernel<<<1, 256, 0, st>>>(c, noise, d_imu, k);
     return cudaGetLastError();
 }
 cudaError_t launch_set_frame(UpdateCtrl* c, cudaStream_t st) {

@@ -232,3 +232,38 @@ def test_tick_on_the_device_equals_the_host_path(lv, O, scene_xaloc):
     assert sorted(map(tuple, a.map_points().tolist())) == sorted(map(tuple, b.map_points().tolist()))
     b.device_free(d)
     a.close(); b.close()
+
+
+def test_propagate_on_the_device_equals_the_host_predict(lv, O, scene_xaloc):
+    """esekf::predict (esekfom.hpp:279-384) for a run of IMU samples: one device launch (lv_propagate_device) against the host
+    loop over lv_predict; then update -> propagate -> update with the state never leaving the GPU equals the host-driven
+    sequence."""
+    sc = scene_xaloc
+    rng = np.random.default_rng(2)
+    k = 37
+    acc = np.array([0.2, -0.1, 9.8]) + rng.normal(0, 0.05, (k, 3))
+    gyro = np.array([0.01, -0.02, 0.2]) + rng.normal(0, 0.01, (k, 3))
+    dt = np.full(k, 0.0025) + rng.uniform(0, 1e-4, k)
+    a, b = lv.Localizer(sc.prm), lv.Localizer(sc.prm)
+    for loc in (a, b):
+        loc.map_build(sc.map)
+        loc.set_state(sc.x_prop, sc.P0)
+    for i in range(k):
+        a.predict(acc[i], gyro[i], dt[i])
+    b.propagate_device(acc, gyro, dt)
+    xa, Pa = a.get_state()
+    xb, Pb = b.get_state()
+    assert np.abs(xa - xb).max() < 1e-12 and np.abs(Pa - Pb).max() <= 1e-12 * np.abs(Pa).max()
+    # a tick: correct, add the sweep, propagate, correct again
+    for loc in (a, b):
+        loc.set_state(sc.x_prop, sc.P0)
+    sta, xa, Pa, la = a.correct(sc.sweep)
+    for i in range(8):
+        a.predict(acc[i], gyro[i], 1e-3)
+    sta, xa, Pa, la = a.correct(sc.sweep)
+    b.correct_device(b.upload(sc.sweep), len(sc.sweep))
+    b.propagate_device(acc[:8], gyro[:8], np.full(8, 1e-3))
+    stb, xb, Pb, lb = b.correct(sc.sweep)
+    assert sta == stb == 0 and len(la) == len(lb)
+    assert np.abs(xa - xb).max() < 1e-9 and np.abs(Pa - Pb).max() <= 1e-8 * np.abs(Pa).max()
+    a.close(); b.close()

@@ -7,6 +7,7 @@ import __graft_entry__ as G, bench
 lv = G.load_package()
 prm = lv.params_from_yaml(lv.CONFIG_DIR + "/xaloc.yaml", max_map_points=bench.MAP_POINTS + 4 * 65536, max_points=65536)
 world, mp, sweeps, x_props, truths = bench.make_scene(lv, 0, n_sweeps=2, prm=prm)
+prm.sort_queries = int(os.environ.get("LV_TIMELINE_SORT", "0"))
 x0, P0 = lv.init_state_host(prm)
 loc = lv.Localizer(prm); loc.map_build(mp)
 d = [loc.upload(s) for s in sweeps]
