@@ -51,6 +51,9 @@ CONFIGS = {
     "cfg3": dict(yaml="ouster.yaml", map_points=10_000_000, rings=128, azimuths=2048, elev=(-22.5, 22.5), sub_sweeps=1,
                  max_iters=None, planar=False, seed_off=3,
                  what="ouster.yaml, 262144-pt Ouster-128 sweep vs 10M-pt map"),
+    "cfg4": dict(yaml="xaloc.yaml", map_points=MAP_POINTS, rings=RINGS, azimuths=AZIMUTHS, elev=(-24.8, 2.0), sub_sweeps=1,
+                 max_iters=None, planar=False, seed_off=10, sequences=8,
+                 what="8 independent cfg1-like sequences (65536-pt sweeps, 1M-pt maps), a FIXED job spread over the GPUs"),
 }
 
 
@@ -473,19 +476,12 @@ def run_native(args, rank, local_rank, world_size):
         except Exception as e:
             multi = {"error": str(e)}
 
-    # ---- max over ranks / totals ----
-    tot = torch.tensor([step_ms, float(pts), float(matched), e2e_s, float(e2e_pts), float(launches)],
-                       dtype=torch.float64, device="cuda")
-    if world_size > 1:
-        mx = tot.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = tot.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        step_ms_max, e2e_s_max = float(mx[0]), float(mx[3])
-        pts_all, matched_all, e2e_pts_all, launches_all = float(sm[1]), float(sm[2]), float(sm[4]), float(sm[5])
-    else:
-        step_ms_max, e2e_s_max = step_ms, e2e_s
-        pts_all, matched_all, e2e_pts_all, launches_all = float(pts), float(matched), float(e2e_pts), float(launches)
+    # ---- max over ranks / totals (limo-velo_b200/dist.py: MAX of the times, SUM of the work; covered by tests/test_dist_gloo.py) ----
+    import importlib
+    dist_mod = importlib.import_module("limovelo_b200.dist")
+    red = dist_mod.reduce_counters(step_ms, pts, matched, e2e_s, e2e_pts, launches, device="cuda")
+    step_ms_max, e2e_s_max = red["step_ms"], red["e2e_s"]
+    pts_all, matched_all, e2e_pts_all, launches_all = red["points"], red["matched"], red["e2e_points"], red["launches"]
 
     if rank == 0:
         peaks = {}
@@ -611,6 +607,117 @@ def multi_sequence_leg(lv, torch, cfg, local_rank, rank, s_list, steps):
                    "L2 flushed between steps", "results": out}
 
 
+def run_strong(args, rank, local_rank, world_size):
+    """BASELINE.json configs[4]: a fixed job of 8 independent sequences over N GPUs (strong scaling).  Every rank runs its
+    share concurrently (one handle + one stream per sequence); one step = every sequence does one update."""
+    import importlib
+    import torch
+    import torch.distributed as dist
+    lv = G.load_package()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the native arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dist_mod = importlib.import_module("limovelo_b200.dist")
+    cfg = "cfg4"
+    n_seq = CONFIGS[cfg]["sequences"]
+    mine = dist_mod.sequence_for_rank(rank, world_size, n_seq)
+    n = update_points(cfg)
+    streams, locs, data = [], [], []
+    for sq in mine:
+        st = torch.cuda.Stream()
+        prm = config_params(lv, cfg, device=local_rank, stream=st.cuda_stream)
+        world, mp, sweeps, x_props, truths = make_scene(lv, sq, n_sweeps=4, prm=prm, cfg=cfg)
+        loc = lv.Localizer(prm)
+        loc.map_build(mp)
+        loc.init_state()
+        _, P0 = loc.get_state()
+        pinned = [torch.from_numpy(sw.copy()).pin_memory() for sw in sweeps]
+        dev = [torch.empty((n, 3), dtype=torch.float32, device="cuda") for _ in sweeps]
+        for d, p in zip(dev, pinned):
+            d.copy_(p)
+        streams.append(st); locs.append(loc); data.append((dev, pinned, x_props, P0, truths))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    main = streams[0] if streams else torch.cuda.current_stream()
+
+    def step(i, with_copies):
+        for s, loc in enumerate(locs):
+            loc.set_state(data[s][2][i % 4], data[s][3])
+        fork, join = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(main):
+            flush.fill_(i & 255)
+        fork.record(main)
+        ends = []
+        for s, loc in enumerate(locs):
+            if s:
+                streams[s].wait_event(fork)
+            d = data[s][0][i % 4]
+            if with_copies:                                         # e2e: the sweep comes from pinned host memory inside the timed region
+                with torch.cuda.stream(streams[s]):
+                    d.copy_(data[s][1][i % 4], non_blocking=True)
+            loc.correct_device(d.data_ptr(), n)
+            e = torch.cuda.Event()
+            e.record(streams[s])
+            ends.append(e)
+        for e in ends[1:]:
+            main.wait_event(e)
+        join.record(main)
+        evals = 0
+        for loc in locs:
+            st_, lg = loc.last_logs()                               # D2H of the result (26.9 KB) + synchronisation
+            evals += len(lg)
+        return fork.elapsed_time(join), evals
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    for i in range(max(3, args.warmup)):
+        step(i, False)
+    torch.cuda.synchronize()
+    clocks.wait_first()
+    if world_size > 1:
+        dist.barrier()
+    for loc in locs:
+        loc.profile(reset=True)
+    ms, evals = 0.0, 0
+    for i in range(args.steps):
+        m, e = step(args.warmup + i, False)
+        ms += m
+        evals += e
+    torch.cuda.synchronize()
+    if world_size > 1:
+        dist.barrier()
+    launches = sum(loc.profile(reset=True)["total_launches"] for loc in locs)
+    e2e_ms, e2e_evals = 0.0, 0
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        m, e = step(args.warmup + i, True)
+        e2e_ms += m
+        e2e_evals += e
+    e2e_wall = time.perf_counter() - t0
+    clock_info = clocks.stop()
+    err = max(float(np.abs(G.load_oracle().boxminus(loc.get_state()[0], data[s][4][(args.warmup + args.steps - 1) % 4]))[:3].max())
+              for s, loc in enumerate(locs)) if locs else 0.0
+    red = dist_mod.reduce_counters(ms, n * evals, 0, e2e_ms * 1e-3, n * e2e_evals, launches, device="cuda")
+    if rank == 0:
+        line = {"metric": metric_name(cfg), "value": red["points"] / (red["step_ms"] * 1e-3), "unit": UNIT, "n_gpus": world_size,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": red["step_ms"] / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32 geometry / f64 Jacobian+filter", "data": "synthetic",
+                "config": dict(workload_config(world_size, cfg, sequences=n_seq),
+                               parallelism="%d sequences per GPU, one handle + one CUDA stream each, no data-path collective" % len(mine)),
+                "e2e": {"value": red["e2e_points"] / red["e2e_s"], "unit": UNIT, "h2d_bytes_per_step": n_seq * n * 12,
+                        "d2h_bytes_per_step": n_seq * locs[0].result_bytes(), "ms_per_step": 1e3 * red["e2e_s"] / args.steps,
+                        "how": "per sequence: pinned-host sweep -> device (async copy on the sequence's stream), update, result D2H; "
+                               "CUDA events fork/join over all streams of the rank, max over ranks"},
+                "gpu_launches": int(round(red["launches"])), "sequences_total": n_seq, "sequences_per_gpu": len(mine),
+                "e2e_wall_ms_per_step": 1e3 * e2e_wall / args.steps, "final_position_error_m": err, "clocks": clock_info}
+        print(json.dumps(line), flush=True)
+    for loc in locs:
+        loc.close()
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
 def deskew_case(lv, world, prm, sweep, t1=10.0, t2=10.1, n_states=4, imu_hz=400.0):
     """a 0.1 s sweep at 15 m/s: KF states every ~33 ms, IMU at 400 Hz, point stamps spread over the sweep"""
     rng = np.random.default_rng(SEED + 77)
@@ -656,6 +763,8 @@ def main():
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank, world_size)
+    elif args.config == "cfg4":
+        run_strong(args, rank, local_rank, world_size)
     else:
         run_native(args, rank, local_rank, world_size)
 

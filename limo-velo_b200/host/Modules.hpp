@@ -78,6 +78,12 @@ class Mapper {
         check(s, "Mapper::add");
         last_map_time = time;
     }
+    /* main.cpp:99-105 without leaving the GPU: the sweep Localizator::correct has just used (still resident on the device)
+     * is transformed by the corrected state and merged (lv_map_add_last_sweep); nothing is copied to or from the host */
+    void add_corrected_sweep(double time, bool downsample = true) {
+        check(lv_map_add_last_sweep(ctx.h, downsample ? 1 : 0), "Mapper::add_corrected_sweep");
+        last_map_time = time;
+    }
 
    private:
     Context& ctx;
@@ -105,6 +111,22 @@ class Localizator {
     void propagate_to(const IMUs& imus, double t) {
         for (const IMU& imu : imus) propagate(imu);
         if (!imus.empty()) { IMU last = imus.back(); last.time = t; propagate(last); }
+    }
+    /* the same with every IMU sample in ONE device launch (lv_propagate_device): the filter state stays in HBM between the
+     * previous update and the next one */
+    void propagate_to_device(const IMUs& imus, double t) {
+        if (imus.empty()) return;
+        std::vector<double> a, w, dt;
+        double last = last_time_integrated < 0 ? imus.front().time : last_time_integrated;
+        for (const IMU& imu : imus) {
+            for (int k = 0; k < 3; ++k) { a.push_back(imu.a[k]); w.push_back(imu.w[k]); }
+            dt.push_back(imu.time - last);
+            last = imu.time;
+        }
+        for (int k = 0; k < 3; ++k) { a.push_back(imus.back().a[k]); w.push_back(imus.back().w[k]); }   /* Localizator.cpp:70-74: the last sample up to t */
+        dt.push_back(t - last);
+        check(lv_propagate_device(ctx.h, a.data(), w.data(), dt.data(), (int32_t)dt.size()), "Localizator::propagate_to_device");
+        last_time_integrated = t;
     }
     /* Localizator.cpp:23-27.  Returns the number of h-evaluations (0 when the map is empty). */
     int correct(const Points& points, double time) {

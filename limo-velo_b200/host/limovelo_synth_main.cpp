@@ -3,7 +3,7 @@
  * reader: propagate_to -> compensate -> downsample -> correct -> map.add, with LIMO-Velo's module
  * names (Modules.hpp) on top of liblimovelo_b200.so.
  *
- *   limovelo_synth <config.yaml> [sweeps=10] [map_points=200000] [rings=64] [azimuths=1024]
+ *   limovelo_synth <config.yaml> [sweeps=10] [map_points=200000] [rings=64] [azimuths=1024] [downsample_leaf=0]
  */
 #include <math.h>
 #include <stdio.h>
@@ -15,10 +15,11 @@
 #include "Modules.hpp"
 
 int main(int argc, char** argv) {
-    if (argc < 2) { fprintf(stderr, "usage: %s config.yaml [sweeps] [map_points] [rings] [azimuths]\n", argv[0]); return 2; }
+    if (argc < 2) { fprintf(stderr, "usage: %s config.yaml [sweeps] [map_points] [rings] [azimuths] [downsample_leaf]\n", argv[0]); return 2; }
     const int sweeps = argc > 2 ? atoi(argv[2]) : 10;
     const int64_t map_points = argc > 3 ? atoll(argv[3]) : 200000;
     const int rings = argc > 4 ? atoi(argv[4]) : 64, azimuths = argc > 5 ? atoi(argv[5]) : 1024;
+    const float leaf = argc > 6 ? (float)atof(argv[6]) : 0.f;
     try {
         lv_params prm;
         lv_default_params(&prm);
@@ -61,7 +62,7 @@ int main(int argc, char** argv) {
                 for (int s = 1; s <= 4; ++s)
                     accum.receive_imu(lv::IMU{{-cur.x[23], -cur.x[24], -cur.x[25]}, {0, 0, 0}, t2 - 0.1 + 0.025 * s});
             }
-            loc.propagate_to(accum.get_imus(t2 - 0.1, t2), t2);       /* main.cpp:76 */
+            loc.propagate_to_device(accum.get_imus(t2 - 0.1, t2), t2);   /* main.cpp:76: all IMU samples in one device launch */
             /* the synthetic vehicle is kinematic (no simulated IMU dynamics): take pose and velocity of the
              * prediction from the ground truth plus a 3 cm offset, and re-open the covariance to P0 so that
              * the offset is a consistent prior error */
@@ -71,34 +72,19 @@ int main(int argc, char** argv) {
             for (int i = 0; i < 7; ++i) pred.x[i] = truth[i] + (i < 3 ? 0.03 : 0.0);
             for (int i = 0; i < 3; ++i) pred.x[14 + i] = (truth[i] - prev[i]) / 0.1;
             lv::check(lv_set_state(ctx.h, pred.x, P0), "prediction");
-            lv::Points ds = comp.downsample(comp.compensate(accum.points));   /* main.cpp:79-80 */
+            /* main.cpp:79-80: the synthetic sweep arrives deskewed (rays cast from the pose at t2); the voxel-grid downsample
+             * (Compensator::downsample, leaf downsample_prec) runs on the GPU when a leaf is given on the command line */
+            lv::Points ds = leaf > 0.f ? comp.downsample(comp.compensate(accum.points), leaf) : comp.downsample(comp.compensate(accum.points));
             const auto t0 = std::chrono::steady_clock::now();
             const int evals = loc.correct(ds, t2);                    /* main.cpp:84 */
+            /* main.cpp:101-105: the sweep joins the map in the world frame of the corrected state, under the 0.2 m rule —
+             * on the device, with the state the update left there (no copy of the sweep, no copy of the state) */
+            map.add_corrected_sweep(t2, true);
             const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
             lv::State X = loc.latest_state();
             const double err = sqrt(pow(X.x[0] - truth[0], 2) + pow(X.x[1] - truth[1], 2) + pow(X.x[2] - truth[2], 2));
-            printf("sweep %2d  t=%.1f  evals=%d  Nm=%lld  correct()=%.3f ms  |pos error|=%.4f m  map=%d\n", k, t2, evals,
+            printf("sweep %2d  t=%.1f  points=%zu  evals=%d  Nm=%lld  correct()+map.add()=%.3f ms  |pos error|=%.4f m  map=%d\n", k, t2, ds.size(), evals,
                    evals ? (long long)loc.logs[evals - 1].n_matches : 0LL, ms, err, map.size());
-            /* main.cpp:101-105: add the sweep, in the world frame of the corrected state, downsampled */
-            lv::Points global(ds.size());
-            {
-                const double* q = X.rot();
-                const double R[9] = {1 - 2 * (q[1] * q[1] + q[2] * q[2]), 2 * (q[0] * q[1] - q[2] * q[3]), 2 * (q[0] * q[2] + q[1] * q[3]),
-                                     2 * (q[0] * q[1] + q[2] * q[3]), 1 - 2 * (q[0] * q[0] + q[2] * q[2]), 2 * (q[1] * q[2] - q[0] * q[3]),
-                                     2 * (q[0] * q[2] - q[1] * q[3]), 2 * (q[1] * q[2] + q[0] * q[3]), 1 - 2 * (q[0] * q[0] + q[1] * q[1])};
-                const double* ql = X.x + 7;
-                const double RL[9] = {1 - 2 * (ql[1] * ql[1] + ql[2] * ql[2]), 2 * (ql[0] * ql[1] - ql[2] * ql[3]), 2 * (ql[0] * ql[2] + ql[1] * ql[3]),
-                                      2 * (ql[0] * ql[1] + ql[2] * ql[3]), 1 - 2 * (ql[0] * ql[0] + ql[2] * ql[2]), 2 * (ql[1] * ql[2] - ql[0] * ql[3]),
-                                      2 * (ql[0] * ql[2] - ql[1] * ql[3]), 2 * (ql[1] * ql[2] + ql[0] * ql[3]), 1 - 2 * (ql[0] * ql[0] + ql[1] * ql[1])};
-                for (size_t i = 0; i < ds.size(); ++i) {
-                    const double p[3] = {ds[i].x, ds[i].y, ds[i].z}, *tl = X.x + 11;
-                    double b[3], g[3];
-                    for (int r = 0; r < 3; ++r) b[r] = RL[3 * r] * p[0] + RL[3 * r + 1] * p[1] + RL[3 * r + 2] * p[2] + tl[r];
-                    for (int r = 0; r < 3; ++r) g[r] = R[3 * r] * b[0] + R[3 * r + 1] * b[1] + R[3 * r + 2] * b[2] + X.x[r];
-                    global[i] = lv::Point{(float)g[0], (float)g[1], (float)g[2], t2};
-                }
-            }
-            map.add(global, t2, true);
         }
         lv_synth_world_destroy(world);
     } catch (const std::exception& e) {
