@@ -11,8 +11,6 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
-#include <time.h>
-#include <unistd.h>
 
 #include <string>
 #include <vector>
@@ -727,70 +725,20 @@ static lv_status run_measure_once(lv_context* h, const double* x, const float* x
     }
     const int grid = measure_grid((int)n);
     if (a.bin_key) { int l = 0; LV_CUDA(launch_bin(a, h->stream, 0, &l)); h->prof.total_launches += l; }
-    static const bool diag_events = getenv("LV_DIAG_EVENTS") != nullptr;   /* diagnosis (tools/diag_hang.sh): which kernel does not finish? */
-    if (diag_events) {
-        struct Ctx { cudaStream_t st; cudaEvent_t ev[6]; int n; } ctx = {h->stream, {}, 0};
-        MeasureProbe probe;
-        probe.ctx = &ctx;
-        probe.at = [](void* p, int) { Ctx* c = static_cast<Ctx*>(p); cudaEventCreateWithFlags(&c->ev[c->n], cudaEventDisableTiming); cudaEventRecord(c->ev[c->n], c->st); c->n++; };
-        LV_CUDA(launch_measure(a, grid, h->stream, &probe, 0, 0));
-        LV_CUDA(launch_reduce_partials(h->d_group_rows, partial_groups(grid), h->d_reduced, h->stream));
-        probe.at(&ctx, 9);
-        const char* names[5] = {"before search", "search", "search-upper", "fit", "reduce"};
-        for (int tick = 0; tick < 200; ++tick) {           /* 20 s */
-            if (cudaEventQuery(ctx.ev[ctx.n - 1]) == cudaSuccess) break;
-            struct timespec ts = {0, 100000000};
-            nanosleep(&ts, nullptr);
-        }
-        for (int k = 0; k < ctx.n; ++k)
-            fprintf(stderr, "[lv diag] event after %-14s: %s\n", names[k], cudaEventQuery(ctx.ev[k]) == cudaSuccess ? "complete" : "NOT complete");
-        fflush(stderr);
-        if (cudaEventQuery(ctx.ev[ctx.n - 1]) != cudaSuccess) { set_error("diag: measurement kernels did not finish in 20 s"); _exit(3); }
-    } else {
     LV_CUDA(launch_measure_timed(h, a, grid, 1, 0, -1, 0));
     LV_CUDA(launch_reduce_partials(h->d_group_rows, partial_groups(grid), h->d_reduced, h->stream));
-    }
     LV_CUDA(cudaMemcpyAsync(h->h_reduced, h->d_reduced, sizeof(double) * 157, cudaMemcpyDeviceToHost, h->stream));
     h->prof.total_launches += 5;
     return LV_OK;
 }
 
-#ifdef LV_PHASE_TRACE
-extern "C" int lv_debug_phases(unsigned* out, int reset);
-#endif
 lv_status lv_measure_reduced(lv_handle h, const double* x, const float* xyz, int64_t n, double* HTH, double* HTh,
                              int64_t* nm) {
     if (!h || !x || !xyz || n <= 0) return LV_ERR_ARG;
     if (nm) *nm = 0;
     if (h->map.empty) return LV_EMPTY_MAP;
-#ifdef LV_PHASE_TRACE
-    lv_debug_phases(nullptr, 1);
-#endif
     lv_status s = run_measure_once(h, x, xyz, n, false, false);
     if (s != LV_OK) return s;
-#ifdef LV_PHASE_TRACE   /* diagnosis build: if the kernels do not finish within 15 s, say which warps sit where, and leave */
-    {
-        int tick = 0;
-        for (; tick < 150 && cudaStreamQuery(h->stream) == cudaErrorNotReady; ++tick) { struct timespec ts = {0, 100000000}; nanosleep(&ts, nullptr); }
-        if (tick >= 150) {
-            static unsigned ph[3 * 16384];
-            const int e = lv_debug_phases(ph, 0);
-            fprintf(stderr, "[lv trace] kernels not finished after 15 s (read-back rc %d)\n", e);
-            const char* kn[3] = {"search", "search-upper", "fit"};
-            for (int k = 0; k < 3; ++k) {
-                int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, other = 0, shown = 0;
-                for (int w = 0; w < 16384; ++w) { const unsigned v = ph[k * 16384 + w]; if ((v & 0x80000000u) || (v & 0xff) > 4) other++; else cnt[v & 0xff]++; }
-                fprintf(stderr, "[lv trace] %-12s warps by phase: none %d | 1: %d | 2: %d | 3: %d | done: %d | in-query: %d\n", kn[k], cnt[0], cnt[1], cnt[2], cnt[3], cnt[4], other);
-                for (int w = 0; w < 16384 && shown < 24; ++w) {
-                    const unsigned v = ph[k * 16384 + w];
-                    if (v != 0 && v != 4u) { fprintf(stderr, "[lv trace]    %s warp %d (block %d): 0x%08x\n", kn[k], w, w / 4, v); ++shown; }
-                }
-            }
-            fflush(stderr);
-            _exit(3);
-        }
-    }
-#endif
     LV_CUDA(cudaStreamSynchronize(h->stream));
     if (HTH) memcpy(HTH, h->h_reduced, sizeof(double) * 144);
     if (HTh) memcpy(HTh, h->h_reduced + 144, sizeof(double) * 12);
@@ -841,32 +789,6 @@ lv_status lv_match_all(lv_handle h, const double* x, const float* xyz, int64_t n
     return LV_OK;
 }
 
-#ifdef LV_DIAG   /* diagnosis build only (tools/k1_isolate.py): host-side helpers, the kernels are the release kernels */
-/* run [set_frame, counter reset, search (+ search-upper if stages >= 2, + fit if stages >= 3)] `reps` times, polling
- * the stream for up to 5 s after each repetition; returns 0, or 1 + the repetition that did not finish */
-int lv_debug_stage_loop(lv_handle h, const double* x, const float* xyz, int64_t n, int reps, int stages) {
-    if (cudaSetDevice(h->prm.device) != cudaSuccess) return -1;
-    cudaMemcpyAsync(h->d_sweep, xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, h->stream);
-    upload_state(h, x, nullptr);
-    h->state_dirty = true;
-    MeasureArgs a = make_measure_args(h, h->d_sweep, n);
-    const int grid = measure_grid((int)n);
-    MeasureKernelShape shape[kMeasureKernels];
-    measure_kernel_shapes(a, grid, shape);
-    for (int r = 0; r < reps; ++r) {
-        launch_set_frame(h->d_ctrl, h->stream);
-        cudaMemsetAsync(a.hard_count, 0, kCounters * sizeof(uint32_t), h->stream);
-        void* args[1] = {&a};
-        for (int k = 0; k < stages && k < 3; ++k)
-            cudaLaunchKernel(shape[k].func, dim3(shape[k].grid), dim3(shape[k].block), args, 0, h->stream);
-        int tick = 0;
-        for (; tick < 5000 && cudaStreamQuery(h->stream) == cudaErrorNotReady; ++tick) { struct timespec ts = {0, 1000000}; nanosleep(&ts, nullptr); }
-        if (tick >= 5000) return 1 + r;
-        if (cudaGetLastError() != cudaSuccess) return -2;
-    }
-    return 0;
-}
-#endif
 
 /* ---- utilities ------------------------------------------------------------------------------- */
 void* lv_host_alloc(int64_t bytes) {

@@ -266,7 +266,7 @@ cudaError_t map_add(MapBuffers& b, const float* d_xyz, int64_t n, int downsample
     lv_map_merge_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(m, b.skeys_alt, b.svals_alt, n32, d_xyz, (uint32_t)b.n_inserted, downsample);
     /* touched <= n voxels, dirty <= 27 n: fixed grids striding over the device-side counts */
     uint64_t dil = ((uint64_t)n * 27 + 255) / 256;
-    dil = dil < 1 ? 1 : (dil > 148u * 32u ? 148u * 32u : dil);
+    dil = dil < 1 ? 1 : (dil > 148u * 8u ? 148u * 8u : dil);
     lv_map_dilate_kernel<<<(unsigned)dil, 256, 0, st>>>(m);
     uint64_t hal = ((uint64_t)n * 27 + 7) / 8;
     hal = hal < 1 ? 1 : (hal > 148u * 64u ? 148u * 64u : hal);

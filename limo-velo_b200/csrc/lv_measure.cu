@@ -40,12 +40,6 @@ __device__ long long g_step_clk[64];
 #endif
 #endif
 
-#ifdef LV_PHASE_TRACE   /* diagnosis build: every warp of the measurement kernels stamps the phase it has reached */
-__device__ unsigned g_lv_phase[3][16384];
-#define LV_PHASE(k, v) do { if ((threadIdx.x & 31) == 0) { const unsigned w_ = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; if (w_ < 16384u) g_lv_phase[k][w_] = (v); } } while (0)
-#else
-#define LV_PHASE(k, v)
-#endif
 #include <cub/device/device_radix_sort.cuh>
 
 #include "lv_internal.h"
@@ -149,7 +143,6 @@ __global__ void __launch_bounds__(LV_SEARCH_THREADS) lv_search_kernel(const Meas
     const int n_redo = LIST ? (int)a.hard_count[2] : 0;
     const int slot = (int)(((int64_t)blockIdx.x * LV_SEARCH_THREADS + threadIdx.x) / G);
     const int listed = LIST ? (int)a.redo_list[slot] : 0;   /* redo_list holds max_points entries: always readable */
-    LV_PHASE(0, 1u);
     if (done) return;
     int qi = slot;
     bool have = slot < jb.n;
@@ -168,9 +161,7 @@ __global__ void __launch_bounds__(LV_SEARCH_THREADS) lv_search_kernel(const Meas
     }
     Top5 t;
     float region = 0.f;
-    LV_PHASE(0, 2u | (bc << 8));
     const bool settled = level0_scan<Grp>(a.map, g[0], g[1], g[2], a.max_d2, bs, bc, st == 1, t, &region);
-    LV_PHASE(0, 3u);
     if (have && (threadIdx.x & (G - 1)) == 0) {
         store_neighbours(a, qi, t);
         const bool hard = st == 2 || (st == 1 && !settled);
@@ -180,7 +171,6 @@ __global__ void __launch_bounds__(LV_SEARCH_THREADS) lv_search_kernel(const Meas
             a.hard_list[(size_t)b * a.hard_seg + atomicAdd(a.hard_count + 4 + b, 1u)] = (uint32_t)qi;
         }
     }
-    LV_PHASE(0, 4u);
     LV_TL_END(2);
 }
 
@@ -487,7 +477,6 @@ __global__ void __launch_bounds__(128) lv_search_rings_kernel(const MeasureArgs 
         }
         const uint32_t before = __shfl_sync(0xffffffffu, incl - cnt, lo);
         const int qi = (int)a.hard_list[(size_t)lo * a.hard_seg + (h - before)];
-        LV_PHASE(1, 0x80000000u | (unsigned)qi);
         float g[3];
         rt_apply(T, jb.xyz[3 * qi], jb.xyz[3 * qi + 1], jb.xyz[3 * qi + 2], g);
         const int2 prev = a.nn_b[qi];   /* level 0's (uncertified) 5th distance bounds the answer from above */
@@ -501,7 +490,6 @@ __global__ void __launch_bounds__(128) lv_search_rings_kernel(const MeasureArgs 
             store_ref(a, qi, g, outsider_bound(u.d5, region));
         }
     }
-    LV_PHASE(1, 4u);
     LV_TL_END(3);
 }
 
@@ -556,7 +544,6 @@ __global__ void __launch_bounds__(kMeasureThreads, 4) lv_fit_kernel(const Measur
     pdl_wait();                 /* the neighbour lists */
     pdl_trigger();
     LV_TL_WORK(a.ctrl, 4);
-    LV_PHASE(2, 1u);
     if (done) return;
 
     double acc = 0.0;
@@ -668,7 +655,6 @@ __global__ void __launch_bounds__(kMeasureThreads, 4) lv_fit_kernel(const Measur
             a.group_rows[(size_t)grp * kPartialStride + tid] = sum;
         }
     }
-    LV_PHASE(2, 4u);
     LV_TL_END(4);
 }
 
@@ -888,9 +874,8 @@ cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st, cons
     static const bool dbg_sync = getenv("LV_DEBUG_SYNC") != nullptr;   /* diagnosis: name the kernel that does not finish */
     if (dbg_sync) { cudaStreamSynchronize(st); fprintf(stderr, "[lv] search done\n"); fflush(stderr); }
     if (probe) probe->at(probe->ctx, 1);
-    static const int upper_grid = getenv("LV_UPPER_GRID") ? atoi(getenv("LV_UPPER_GRID")) : 148 * 2;   /* diagnosis override */
-    launch_k(lv_search_rings_kernel, upper_grid > 0 ? upper_grid : 148 * 2, 128, st, pdl != 0, a);
-    if (dbg_sync) { cudaStreamSynchronize(st); fprintf(stderr, "[lv] search-upper done\n"); fflush(stderr); }
+    launch_k(lv_search_rings_kernel, 148 * 2, 128, st, pdl != 0, a);
+    if (dbg_sync) { cudaStreamSynchronize(st); fprintf(stderr, "[lv] search-rings done\n"); fflush(stderr); }
     if (probe) probe->at(probe->ctx, 2);
     launch_k(lv_fit_kernel, grid + (a.prep ? 1 : 0), kMeasureThreads, st, pdl != 0, a);
     if (dbg_sync) { cudaStreamSynchronize(st); fprintf(stderr, "[lv] fit done\n"); fflush(stderr); }
@@ -944,19 +929,6 @@ cudaError_t launch_l2_flush(void* buf, size_t bytes, cudaStream_t st) {
 
 }  // namespace lv
 
-#ifdef LV_PHASE_TRACE
-/* readable while a kernel hangs: copies on a stream of their own */
-extern "C" int lv_debug_phases(unsigned* out /*3 x 16384*/, int reset) {
-    cudaStream_t s2;
-    if (cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking) != cudaSuccess) return -1;
-    int e;
-    if (reset) { static unsigned zeros[3 * 16384]; e = (int)cudaMemcpyToSymbolAsync(g_lv_phase, zeros, sizeof(zeros), 0, cudaMemcpyHostToDevice, s2); }
-    else e = (int)cudaMemcpyFromSymbolAsync(out, g_lv_phase, sizeof(unsigned) * 3 * 16384, 0, cudaMemcpyDeviceToHost, s2);
-    if (!e) e = (int)cudaStreamSynchronize(s2);
-    cudaStreamDestroy(s2);
-    return e;
-}
-#endif
 #ifdef LV_STEP_TIMING
 extern "C" int lv_debug_step_clocks(long long* out) {
     return (int)cudaMemcpyFromSymbol(out, g_step_clk, sizeof(long long) * 64);

@@ -357,6 +357,20 @@ LV_HD_NOINLINE void map_merge_run(const VoxelMapRW& m, const uint32_t* skeys, co
         changed = true;
     } else {
         const float ds = m.grid.ds;
+        /* the cell of every own point, once (cell_coord_old costs three IEEE divisions per point): 5 bits per point, packed;
+         * own extents beyond kCellCache points (dense first-sweep voxels) fall back to recomputing */
+        enum { kCellCache = 48 };
+        const int k = m.grid.k;
+        const int vx0 = ((int)((uint32_t)key & 0x1FFFFFu) - LV_KEY_BIAS) * k, vy0 = ((int)((uint32_t)(key >> 21) & 0x1FFFFFu) - LV_KEY_BIAS) * k,
+                  vz0 = ((int)((uint32_t)(key >> 42) & 0x1FFFFFu) - LV_KEY_BIAS) * k;
+        uint8_t ocell[kCellCache];
+        const bool cached = cnt + groups <= (uint32_t)kCellCache;   /* every group appends at most one point */
+        if (cached)
+            for (uint32_t t = 0; t < cnt; ++t) {
+                const float4 q = own[t];
+                const int lx = cell_coord_old(q.x, ds) - vx0, ly = cell_coord_old(q.y, ds) - vy0, lz = cell_coord_old(q.z, ds) - vz0;
+                ocell[t] = (lx < 0 || ly < 0 || lz < 0 || lx >= k || ly >= k || lz >= k) ? (uint8_t)255 : (uint8_t)(lx + k * (ly + k * lz));   /* 255: an ulp outside */
+            }
         uint32_t g0 = j;
         while (g0 < e) {
             uint32_t g1 = g0 + 1;
@@ -365,12 +379,16 @@ LV_HD_NOINLINE void map_merge_run(const VoxelMapRW& m, const uint32_t* skeys, co
             const uint32_t s0 = svals[g0];
             const int cx = cell_coord(xyz[3 * (size_t)s0], ds), cy = cell_coord(xyz[3 * (size_t)s0 + 1], ds),
                       cz = cell_coord(xyz[3 * (size_t)s0 + 2], ds);
+            const int lcx = cx - vx0, lcy = cy - vy0, lcz = cz - vz0;
+            const uint8_t gcell = (lcx < 0 || lcy < 0 || lcz < 0 || lcx >= k || lcy >= k || lcz >= k) ? (uint8_t)254 : (uint8_t)(lcx + k * (lcy + k * lcz));
             int best_old = -1;
             uint32_t n_old = 0;
             float best_d = INFINITY;
             for (uint32_t t = 0; t < cnt; ++t) {
                 const float4 q = own[t];
-                if (cell_coord_old(q.x, ds) != cx || cell_coord_old(q.y, ds) != cy || cell_coord_old(q.z, ds) != cz) continue;
+                const bool in_cell = cached ? ocell[t] == gcell
+                                            : (cell_coord_old(q.x, ds) == cx && cell_coord_old(q.y, ds) == cy && cell_coord_old(q.z, ds) == cz);
+                if (!in_cell) continue;
                 ++n_old;
                 const float d = cell_centre_dist(q.x, q.y, q.z, cx, cy, cz, ds);
                 if (best_old < 0 || d < best_d) { best_old = (int)t; best_d = d; }   /* among old points: first strict minimum */
@@ -382,16 +400,25 @@ LV_HD_NOINLINE void map_merge_run(const VoxelMapRW& m, const uint32_t* skeys, co
                 const bool take = (best_old < 0 && best_new < 0) ? true : !(best_d < d);   /* a new point replaces unless the kept one is strictly closer */
                 if (take) { best_new = (int)src; best_d = d; }
             }
-            if (best_new >= 0 || n_old > 1) {
+            bool same = false;                        /* the winner is the point the cell already holds (a re-observed static scene): nothing changes */
+            if (best_new >= 0 && n_old == 1) {
+                const float4 q = own[best_old];
+                same = q.x == xyz[3 * (size_t)best_new] && q.y == xyz[3 * (size_t)best_new + 1] && q.z == xyz[3 * (size_t)best_new + 2];
+            }
+            if ((best_new >= 0 || n_old > 1) && !same) {
                 const float4 w = best_new >= 0 ? make_point(xyz[3 * (size_t)best_new], xyz[3 * (size_t)best_new + 1],
                                                             xyz[3 * (size_t)best_new + 2], id_base + (uint32_t)best_new)
                                                : own[best_old];
                 uint32_t wr = 0;
                 for (uint32_t t = 0; t < cnt; ++t) {
                     const float4 q = own[t];
-                    if (cell_coord_old(q.x, ds) == cx && cell_coord_old(q.y, ds) == cy && cell_coord_old(q.z, ds) == cz) continue;
+                    const bool in_cell = cached ? ocell[t] == gcell
+                                                : (cell_coord_old(q.x, ds) == cx && cell_coord_old(q.y, ds) == cy && cell_coord_old(q.z, ds) == cz);
+                    if (in_cell) continue;
+                    if (cached) ocell[wr] = ocell[t];
                     own[wr++] = q;
                 }
+                if (cached) ocell[wr] = gcell;
                 own[wr++] = w;
                 cnt = wr;
                 changed = true;

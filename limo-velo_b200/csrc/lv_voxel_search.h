@@ -318,12 +318,15 @@ LV_HD void knn5_rings(const VoxelMapView& m, float gx, float gy, float gz, float
  *      candidate list in shared memory (count, scan, write: deterministic order)
  *   3. the candidates, 32 at a time: one slot probe per lane, a warp scan of the counts flattens their own points into
  *      one index range, the lanes stride over it with four independent loads in flight
- * A query that knows nothing yet (no bucket at level 0: bound0 = the search radius) first looks at rings <= 3 only;
- * what it finds there usually shrinks the bound so much that the outer rings are pruned by their box distance.
+ * A query that knows nothing yet (no bucket at level 0: bound0 = the search radius) first derives a bound from the list
+ * itself (the five nearest occupied voxels hold five points), so it too visits a few dozen voxels, not the whole ball.
  */
-enum { kRingBlocksPerLane = 4, kRingCands = 1024 };
+enum { kRingBlocksPerLane = 4, kRingCands = 768, kRingMaxR = 15 };
 struct RingScratch {
-    uint32_t cand[kRingCands];            /* (dx + 64) | (dy + 64) << 8 | (dz + 64) << 16 */
+    uint32_t seg_pk[kRingCands];          /* every occupied voxel in range: (dx + 64) | (dy + 64) << 8 | (dz + 64) << 16         */
+    float seg_d2[kRingCands];             /* their box distances                                                             */
+    uint32_t cand[kRingCands];            /* the candidates of the current pass, dense                                        */
+    float axis_d2[3][2 * kRingMaxR + 1];  /* squared per-axis part of the box distance for offsets -r .. r                    */
 };
 __device__ __forceinline__ void rings_process_candidates(const VoxelMapView& m, const RingScratch* sm, uint32_t n_cand, int hx, int hy, int hz,
                                                          float gx, float gy, float gz, Top5& loc) {
@@ -396,7 +399,7 @@ __device__ __forceinline__ void knn5_rings_warp(const VoxelMapView& m, float gx,
     const int x0 = vx0 >> 2, y0 = vy0 >> 2, z0 = vz0 >> 2;
     const int nx = (vx1 >> 2) - x0 + 1, ny = (vy1 >> 2) - y0 + 1, nz = (vz1 >> 2) - z0 + 1;
     const int nb = nx * ny * nz;
-    if (nb > 32 * kRingBlocksPerLane) {               /* a range no 2 m search produces: the single-lane form, on lane 0 */
+    if (nb > 32 * kRingBlocksPerLane || r > kRingMaxR) {   /* a range no 2 m search produces: the single-lane form, on lane 0 */
         Top5 t1;
         top5_init(t1, bound);
         float reg = bound;
@@ -413,89 +416,98 @@ __device__ __forceinline__ void knn5_rings_warp(const VoxelMapView& m, float gx,
         const int bi = lane + 32 * u;
         mk[u] = bi < nb ? block_find(m, voxel_key((uint32_t)(x0 + bi % nx), (uint32_t)(y0 + (bi / nx) % ny), (uint32_t)(z0 + bi / (nx * ny)))) : 0ull;
     }
-    Top5 loc;
-    top5_init(loc, bound);
-    /* passes over ring intervals [rlo, rhi]: one pass when level 0 left a bound, rings <= 3 first when it did not */
-    const bool blind = !(bound0 < max_d2);
-    int rlo = 0, rhi = (blind && r > 3) ? 3 : r;
-    for (;;) {
-        /* 2. candidates of this pass: count, scan, write */
-        uint32_t cnt = 0;
+    /* per-axis parts of the box distance (voxel_box_d2, one table entry per offset) */
+    for (int e = lane; e < 3 * (2 * r + 1); e += 32) {
+        const int a = e / (2 * r + 1), d = e - a * (2 * r + 1) - r;
+        float v = d < 0 ? h.lo[a] + (float)(-d - 1) * h.edge : (d > 0 ? h.hi[a] + (float)(d - 1) * h.edge : 0.f);
+        v = d == 0 ? 0.f : v - h.slack * (float)(d < 0 ? -d : d);
+        v = v > 0.f ? v : 0.f;
+        sm->axis_d2[a][d + r] = v * v;
+    }
+    __syncwarp();
+    /* 2. the occupied voxels of the range whose box lies inside the bound, with their box distances, as ONE dense list
+     * (two walks over the set bits of this lane's masks: count, warp scan, write — the order is lane-major and
+     * deterministic); the passes below only filter this list */
+    uint32_t n_list = 0;
+    {
+        uint32_t mine = 0, at = 0;
 #pragma unroll
         for (int pass = 0; pass < 2; ++pass) {
-            uint32_t at = 0;
             if (pass == 1) {
-                uint32_t incl = cnt;
+                uint32_t incl = mine;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
                     if (lane >= d) incl += v;
                 }
-                at = incl - cnt;
-                cnt = __shfl_sync(0xffffffffu, incl, 31);            /* from here on: the warp's total */
+                at = incl - mine;
+                n_list = __shfl_sync(0xffffffffu, incl, 31);
+                if (n_list > (uint32_t)kRingCands) break;
             }
 #pragma unroll
             for (int u = 0; u < kRingBlocksPerLane; ++u) {
                 unsigned long long mm = mk[u];
                 const int bi = lane + 32 * u;
-                const int cbx = (x0 + bi % nx) * 4, cby = (y0 + (bi / nx) % ny) * 4, cbz = (z0 + bi / (nx * ny)) * 4;
+                const int cbx = (x0 + bi % nx) * 4 - hx, cby = (y0 + (bi / nx) % ny) * 4 - hy, cbz = (z0 + bi / (nx * ny)) * 4 - hz;
                 while (mm) {
                     const int c = __ffsll((long long)mm) - 1;
                     mm &= mm - 1ull;
-                    const int dx = cbx + (c & 3) - hx, dy = cby + ((c >> 2) & 3) - hy, dz = cbz + (c >> 4) - hz;
-                    const int ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy, az = dz < 0 ? -dz : dz;
-                    const int cheb = ax > ay ? (ax > az ? ax : az) : (ay > az ? ay : az);
-                    if (cheb < rlo || cheb > rhi || !(voxel_box_d2(h, dx, dy, dz) < bound)) continue;
-                    if (pass == 0) ++cnt;
-                    else { if (at < (uint32_t)kRingCands) sm->cand[at] = (uint32_t)(dx + 64) | ((uint32_t)(dy + 64) << 8) | ((uint32_t)(dz + 64) << 16); ++at; }
+                    const int dx = cbx + (c & 3), dy = cby + ((c >> 2) & 3), dz = cbz + (c >> 4);
+                    if (dx < -r || dx > r || dy < -r || dy > r || dz < -r || dz > r) continue;
+                    const float d2 = (sm->axis_d2[0][dx + r] + sm->axis_d2[1][dy + r]) + sm->axis_d2[2][dz + r];   /* == voxel_box_d2(h, dx, dy, dz) */
+                    if (!(d2 < bound)) continue;
+                    if (pass == 0) ++mine;
+                    else {
+                        sm->seg_pk[at] = (uint32_t)(dx + 64) | ((uint32_t)(dy + 64) << 8) | ((uint32_t)(dz + 64) << 16);
+                        sm->seg_d2[at] = d2;
+                        ++at;
+                    }
                 }
             }
         }
-        __syncwarp();
-        if (cnt > (uint32_t)kRingCands) {            /* more occupied voxels in range than the list holds (volumetric map, tiny voxels) */
-            Top5 t1;
-            top5_init(t1, bound);
-            float reg = bound;
-            if (lane == 0) knn5_rings<GroupSerial>(m, gx, gy, gz, max_d2, bound0, t1, &reg);
-            broadcast_top5(t1, 0);
-            out = t1;
-            if (region_d2) *region_d2 = __shfl_sync(0xffffffffu, reg, 0);
-            return;
-        }
-        /* 3. probe + scan */
-        rings_process_candidates(m, sm, cnt, hx, hy, hz, gx, gy, gz, loc);
-        __syncwarp();
-        if (rhi >= r) break;
-        /* blind query, inner rings done: what was found bounds the rest */
-        Top5 t;
-        GroupWarp::merge(loc, bound, t);
-        float gap = h.lo[0] < h.hi[0] ? h.lo[0] : h.hi[0];
-        gap = gap < h.lo[1] ? gap : h.lo[1]; gap = gap < h.hi[1] ? gap : h.hi[1];
-        gap = gap < h.lo[2] ? gap : h.lo[2]; gap = gap < h.hi[2] ? gap : h.hi[2];
-        float seen = (float)rhi * h.edge + gap - h.slack * (float)(rhi + 1);      /* everything closer than this has been looked at */
-        seen = seen > 0.f ? seen : 0.f;
-        if (t.i4 >= 0 && t.d4 <= seen * seen) {       /* five found inside the certified radius: final */
-            out = t;
-            if (region_d2) *region_d2 = seen * seen < bound ? seen * seen : bound;
-            return;
-        }
-        if (t.i4 >= 0) {                              /* five found: nothing beyond their 5th distance (plus the reuse margin) matters */
-            float nbnd = nextafterf(t.d4, INFINITY);
-            const float wide = t.d4 * 1.21f;
-            nbnd = nbnd > wide ? nbnd : wide;
-            bound = nbnd < bound ? nbnd : bound;
-        }
-        /* put the five back (lane 0) and go on with the outer rings */
-        top5_init(loc, bound);
-        if (lane == 0) {
-            loc = t;                                  /* placeholders (id -1) carry the bound */
-            if (loc.i0 < 0) loc.d0 = bound; if (loc.i1 < 0) loc.d1 = bound; if (loc.i2 < 0) loc.d2 = bound;
-            if (loc.i3 < 0) loc.d3 = bound; if (loc.i4 < 0) loc.d4 = bound;
-        }
-        rlo = rhi + 1;
-        rhi = r;
     }
-    if (region_d2) *region_d2 = bound;
+    __syncwarp();
+    if (n_list > (uint32_t)kRingCands) {              /* more occupied voxels in range than the list holds (volumetric map, tiny voxels) */
+        Top5 t1;
+        top5_init(t1, bound);
+        float reg = bound;
+        if (lane == 0) knn5_rings<GroupSerial>(m, gx, gy, gz, max_d2, bound0, t1, &reg);
+        broadcast_top5(t1, 0);
+        out = t1;
+        if (region_d2) *region_d2 = __shfl_sync(0xffffffffu, reg, 0);
+        return;
+    }
+    /* A query that knows nothing (no bucket at level 0: bound0 = the search radius) would have to visit every occupied voxel
+     * within 2 m.  The list tells it better: every listed voxel holds at least one point, so the five voxels with the smallest
+     * box distances hold five points no farther than (5th smallest box distance + the voxel diagonal) — an upper bound of the
+     * 5th neighbour distance, and the only voxels that can matter are those whose box lies inside it. */
+    if (!(bound0 < max_d2)) {
+        Top5 sel;
+        top5_init(sel, bound);
+        for (uint32_t i = (uint32_t)lane; i < n_list; i += 32) top5_insert(sel, sm->seg_d2[i], (int)i);
+        Top5 s5;
+        GroupWarp::merge(sel, bound, s5);
+        if (s5.i4 >= 0) {
+            const float reach = (fsqrt(s5.d4) + h.slack * (float)(r + 1) + 1.7320509f * h.edge) * 1.0001f;
+            const float b1 = reach * reach;
+            bound = b1 < bound ? b1 : bound;
+        }
+    }
+    Top5 loc;
+    top5_init(loc, bound);
+    /* the candidates: the listed voxels inside the bound, in list order */
+    uint32_t total = 0;
+    for (uint32_t i0 = 0; i0 < n_list; i0 += 32) {
+        const uint32_t i = i0 + (uint32_t)lane;
+        const bool sel = i < n_list && sm->seg_d2[i] < bound;
+        const unsigned bal = __ballot_sync(0xffffffffu, sel);
+        if (sel) sm->cand[total + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = sm->seg_pk[i];
+        total += (uint32_t)__popc(bal);
+    }
+    __syncwarp();
+    /* 3. probe + scan, one merge */
+    rings_process_candidates(m, sm, total, hx, hy, hz, gx, gy, gz, loc);
+    if (region_d2) *region_d2 = bound;     /* every voxel whose box lies inside the bound has been visited */
     GroupWarp::merge(loc, bound, out);
 }
 #endif
