@@ -266,12 +266,20 @@ lv_status lv_create(const lv_params* p, lv_handle* out) {
     LV_CREATE_CUDA(cudaMalloc(&h->d_hard_list, sizeof(uint32_t) * ((size_t)kHardBuckets * hard_segment(p->max_points) + kCounters)));
     LV_CREATE_CUDA(cudaMalloc(&h->d_ref, sizeof(float4) * p->max_points));
     LV_CREATE_CUDA(cudaMalloc(&h->d_redo, sizeof(uint32_t) * (p->max_points + 64)));   /* + one block of slack: read speculatively */
+    /* hand-over buffers start defined: lv_search_kernel<.., LIST> reads redo_list[] before it knows the list's length, and a
+     * first update's reuse kernel must not see stale neighbours (also keeps compute-sanitizer initcheck quiet) */
+    LV_CREATE_CUDA(cudaMemset(h->d_redo, 0, sizeof(uint32_t) * (p->max_points + 64)));
+    LV_CREATE_CUDA(cudaMemset(h->d_nn_a, 0xFF, sizeof(int4) * p->max_points));
+    LV_CREATE_CUDA(cudaMemset(h->d_nn_b, 0xFF, sizeof(int2) * p->max_points));
+    LV_CREATE_CUDA(cudaMemset(h->d_ref, 0, sizeof(float4) * p->max_points));
+    LV_CREATE_CUDA(cudaMemset(h->d_hard_list, 0, sizeof(uint32_t) * ((size_t)kHardBuckets * hard_segment(p->max_points) + kCounters)));
     if (p->sort_queries) {
         LV_CREATE_CUDA(cudaMalloc(&h->d_bin_key, sizeof(uint32_t) * p->max_points));
         LV_CREATE_CUDA(cudaMalloc(&h->d_bin_val, sizeof(uint32_t) * p->max_points));
         LV_CREATE_CUDA(cudaMalloc(&h->d_bin_key_in, sizeof(uint32_t) * p->max_points));
         LV_CREATE_CUDA(cudaMalloc(&h->d_bin_val_in, sizeof(uint32_t) * p->max_points));
         LV_CREATE_CUDA(cudaMalloc(&h->d_redo_flag, p->max_points));
+        LV_CREATE_CUDA(cudaMemset(h->d_redo_flag, 1, p->max_points));
         h->bin_tmp_bytes = bin_sort_tmp_bytes(p->max_points);
         LV_CREATE_CUDA(cudaMalloc(&h->d_bin_tmp, h->bin_tmp_bytes));
     }
@@ -284,7 +292,9 @@ lv_status lv_create(const lv_params* p, lv_handle* out) {
     LV_CREATE_CUDA(cudaMemset(h->d_ctrl, 0, sizeof(UpdateCtrl)));
     LV_CREATE_CUDA(cudaMallocHost(&h->h_ctrl, sizeof(UpdateCtrl)));
     LV_CREATE_CUDA(cudaMalloc(&h->d_partials, sizeof(double) * kPartialStride * (148 * 4 + 8)));
+    LV_CREATE_CUDA(cudaMemset(h->d_partials, 0, sizeof(double) * kPartialStride * (148 * 4 + 8)));
     LV_CREATE_CUDA(cudaMalloc(&h->d_group_rows, sizeof(double) * kPartialStride * 32));
+    LV_CREATE_CUDA(cudaMemset(h->d_group_rows, 0, sizeof(double) * kPartialStride * 32));
     LV_CREATE_CUDA(cudaMalloc(&h->d_group_tickets, sizeof(uint32_t) * 32));
     LV_CREATE_CUDA(cudaMemset(h->d_group_tickets, 0, sizeof(uint32_t) * 32));
     LV_CREATE_CUDA(cudaMalloc(&h->d_reduced, sizeof(double) * 160));

@@ -441,6 +441,9 @@ __global__ void __launch_bounds__(128) lv_reuse_kernel(const MeasureArgs a) {
     LV_TL_END(1);
 }
 
+/* One warp per hard query and a query costs ~10 dependent memory round trips, so the grid gives every hard query of a sweep its
+ * own warp (a 65 536-point sweep has ~1 200): 5 blocks of 4 warps are resident per SM (38 KB of scratch each). */
+enum { kRingsGrid = 148 * 5 };
 /*
  * K1b — search beyond ring 1: one WARP per query K1 could not certify (knn5_rings).  The work list
  * length lives on the device; a fixed grid strides over it, so no host round trip is needed.
@@ -823,7 +826,7 @@ void measure_kernel_shapes(const MeasureArgs& a, int grid, MeasureKernelShape ou
     const int group = search_group();
     out[0].func = search_kernel_ptr<false>(group);
     out[0].grid = (unsigned)search_grid(a, group); out[0].block = LV_SEARCH_THREADS;
-    out[1].func = (const void*)lv_search_rings_kernel; out[1].grid = 148 * 2; out[1].block = 128;
+    out[1].func = (const void*)lv_search_rings_kernel; out[1].grid = kRingsGrid; out[1].block = 128;
     out[2].func = (const void*)lv_fit_kernel; out[2].grid = (unsigned)(grid + (a.prep ? 1 : 0)); out[2].block = kMeasureThreads;
     out[3].func = search_kernel_ptr<true>(group); out[3].grid = out[0].grid; out[3].block = LV_SEARCH_THREADS;
     out[4].func = (const void*)lv_reuse_kernel; out[4].grid = (unsigned)((a.n + 127) / 128 > 0 ? (a.n + 127) / 128 : 1); out[4].block = 128;
@@ -874,7 +877,7 @@ cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st, cons
     static const bool dbg_sync = getenv("LV_DEBUG_SYNC") != nullptr;   /* diagnosis: name the kernel that does not finish */
     if (dbg_sync) { cudaStreamSynchronize(st); fprintf(stderr, "[lv] search done\n"); fflush(stderr); }
     if (probe) probe->at(probe->ctx, 1);
-    launch_k(lv_search_rings_kernel, 148 * 2, 128, st, pdl != 0, a);
+    launch_k(lv_search_rings_kernel, kRingsGrid, 128, st, pdl != 0, a);
     if (dbg_sync) { cudaStreamSynchronize(st); fprintf(stderr, "[lv] search-rings done\n"); fflush(stderr); }
     if (probe) probe->at(probe->ctx, 2);
     launch_k(lv_fit_kernel, grid + (a.prep ? 1 : 0), kMeasureThreads, st, pdl != 0, a);

@@ -308,14 +308,26 @@ LV_HD void knn5_rings(const VoxelMapView& m, float gx, float gy, float gz, float
     Grp::merge(loc, bound, out);
 }
 
+/* The bits of a 4x4x4 block (bit = x + 4 y + 16 z) whose voxel offsets (cbx + x, cby + y, cbz + z) lie in [-r, r]^3. */
+LV_HD unsigned long long block_cube_mask(int cbx, int cby, int cbz, int r) {
+    const int xl = -r - cbx > 0 ? -r - cbx : 0, xh = r - cbx < 3 ? r - cbx : 3;
+    const int yl = -r - cby > 0 ? -r - cby : 0, yh = r - cby < 3 ? r - cby : 3;
+    const int zl = -r - cbz > 0 ? -r - cbz : 0, zh = r - cbz < 3 ? r - cbz : 3;
+    if (xl > xh || yl > yh || zl > zh) return 0ull;
+    const uint32_t nibble = (0xFu >> (3 - xh)) & (0xFu << xl) & 0xFu;                       /* x in [xl, xh]        */
+    const uint32_t rows = (0xFFFFu >> (4 * (3 - yh))) & (0xFFFFu << (4 * yl)) & 0xFFFFu;   /* y in [yl, yh], all x */
+    const unsigned long long slices = (~0ull >> (16 * (3 - zh))) & (~0ull << (16 * zl));   /* z in [zl, zh]        */
+    return (0x1111111111111111ull * nibble) & (0x0001000100010001ull * rows) & slices;
+}
+
 #if defined(__CUDACC__)
 /*
  * knn5_rings for one WARP (same voxel set, same result as the single-lane form above), arranged so that a query costs a
  * handful of dependent memory round trips:
  *   1. the occupancy masks of all blocks overlapping the voxel range (<= 128: four per lane, kept in registers)
- *   2. every lane walks the SET bits of its masks (work proportional to the occupied voxels, not to the volume of the
- *      range), keeps the voxels of the wanted rings whose box lies inside the bound, and the warp compacts them into a
- *      candidate list in shared memory (count, scan, write: deterministic order)
+ *   2. every lane clips its masks to the cube of the wanted rings (block_cube_mask: no walk), walks the SET bits that remain
+ *      (work proportional to the occupied voxels of the cube, not to its volume), keeps the voxels whose box lies inside the
+ *      bound, and the warp compacts them into a candidate list in shared memory (count, scan, write: deterministic order)
  *   3. the candidates, 32 at a time: one slot probe per lane, a warp scan of the counts flattens their own points into
  *      one index range, the lanes stride over it with four independent loads in flight
  * A query that knows nothing yet (no bucket at level 0: bound0 = the search radius) first derives a bound from the list
@@ -430,38 +442,45 @@ __device__ __forceinline__ void knn5_rings_warp(const VoxelMapView& m, float gx,
      * deterministic); the passes below only filter this list */
     uint32_t n_list = 0;
     {
-        uint32_t mine = 0, at = 0;
+        /* pass 0: clip every mask to the cube of the wanted rings (three nibble/row/slice patterns, no walk), then drop the
+         * voxels whose box lies outside the bound; pass 1 writes the survivors */
+        uint32_t mine = 0;
 #pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-            if (pass == 1) {
-                uint32_t incl = mine;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += v;
-                }
-                at = incl - mine;
-                n_list = __shfl_sync(0xffffffffu, incl, 31);
-                if (n_list > (uint32_t)kRingCands) break;
+        for (int u = 0; u < kRingBlocksPerLane; ++u) {
+            const int bi = lane + 32 * u;
+            const int cbx = (x0 + bi % nx) * 4 - hx, cby = (y0 + (bi / nx) % ny) * 4 - hy, cbz = (z0 + bi / (nx * ny)) * 4 - hz;
+            unsigned long long mm = mk[u] & block_cube_mask(cbx, cby, cbz, r), keep = 0ull;
+            while (mm) {
+                const int c = __ffsll((long long)mm) - 1;
+                const unsigned long long bit = mm & (0ull - mm);
+                mm ^= bit;
+                const float d2 = (sm->axis_d2[0][cbx + (c & 3) + r] + sm->axis_d2[1][cby + ((c >> 2) & 3) + r]) + sm->axis_d2[2][cbz + (c >> 4) + r];   /* == voxel_box_d2(h, dx, dy, dz) */
+                if (d2 < bound) keep |= bit;
             }
+            mk[u] = keep;
+            mine += (uint32_t)__popcll(keep);
+        }
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += v;
+        }
+        uint32_t at = incl - mine;
+        n_list = __shfl_sync(0xffffffffu, incl, 31);
+        if (n_list <= (uint32_t)kRingCands) {
 #pragma unroll
             for (int u = 0; u < kRingBlocksPerLane; ++u) {
-                unsigned long long mm = mk[u];
                 const int bi = lane + 32 * u;
                 const int cbx = (x0 + bi % nx) * 4 - hx, cby = (y0 + (bi / nx) % ny) * 4 - hy, cbz = (z0 + bi / (nx * ny)) * 4 - hz;
+                unsigned long long mm = mk[u];
                 while (mm) {
                     const int c = __ffsll((long long)mm) - 1;
                     mm &= mm - 1ull;
                     const int dx = cbx + (c & 3), dy = cby + ((c >> 2) & 3), dz = cbz + (c >> 4);
-                    if (dx < -r || dx > r || dy < -r || dy > r || dz < -r || dz > r) continue;
-                    const float d2 = (sm->axis_d2[0][dx + r] + sm->axis_d2[1][dy + r]) + sm->axis_d2[2][dz + r];   /* == voxel_box_d2(h, dx, dy, dz) */
-                    if (!(d2 < bound)) continue;
-                    if (pass == 0) ++mine;
-                    else {
-                        sm->seg_pk[at] = (uint32_t)(dx + 64) | ((uint32_t)(dy + 64) << 8) | ((uint32_t)(dz + 64) << 16);
-                        sm->seg_d2[at] = d2;
-                        ++at;
-                    }
+                    sm->seg_pk[at] = (uint32_t)(dx + 64) | ((uint32_t)(dy + 64) << 8) | ((uint32_t)(dz + 64) << 16);
+                    sm->seg_d2[at] = (sm->axis_d2[0][dx + r] + sm->axis_d2[1][dy + r]) + sm->axis_d2[2][dz + r];
+                    ++at;
                 }
             }
         }

@@ -299,6 +299,7 @@ void shim_plane_fit(const float* pts5, float thr, float* abcd, int* ok) {
     *ok = plane_fit(q, thr, abcd) ? 1 : 0;
 }
 int shim_sizeof_iterlog() { return (int)sizeof(IterLog); }
+unsigned long long shim_block_cube_mask(int cbx, int cby, int cbz, int r) { return block_cube_mask(cbx, cby, cbz, r); }
 
 }  // extern "C"
 

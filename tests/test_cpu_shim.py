@@ -231,3 +231,22 @@ def test_incremental_map_without_downsampling_and_scattered_points(O):
     inside = np.isfinite(got["nn_sqd"][:, 4])
     assert not (ref["nn_sqd"][~inside, 4].astype(np.float64) < 4.0).any()
     assert (got["nn_sqd"][inside] == ref["nn_sqd"][inside]).all()
+
+
+def test_block_cube_mask_matches_the_per_bit_test():
+    """block_cube_mask (ring search: the occupancy mask of a 4x4x4 block clipped to the cube of wanted rings) against
+    the per-voxel test it replaces, over every block offset and ring count the search can produce."""
+    import ctypes as C
+    L = S.lib()
+    L.shim_block_cube_mask.restype = C.c_uint64
+    L.shim_block_cube_mask.argtypes = [C.c_int] * 4
+    for r in (1, 2, 3, 5, 8, 15):
+        for cbx in range(-r - 5, r + 3):
+            for cby in (-r - 4, -r - 3, -r, -1, 0, r - 3, r - 1, r, r + 1):
+                for cbz in (-r - 4, -r - 2, -2, 0, r - 2, r, r + 1):
+                    want = 0
+                    for c in range(64):
+                        dx, dy, dz = cbx + (c & 3), cby + ((c >> 2) & 3), cbz + (c >> 4)
+                        if -r <= dx <= r and -r <= dy <= r and -r <= dz <= r:
+                            want |= 1 << c
+                    assert L.shim_block_cube_mask(cbx, cby, cbz, r) == want, (cbx, cby, cbz, r)

@@ -1,8 +1,8 @@
 #!/bin/bash
-# round 2, call F: tests + timeline + cfg1 bench after ring search v3 and the cheaper map merge
+# round 2, call H: tests + timeline + benches after clipping the block masks in the ring search
 set -u
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
-OUT=gpurun_out/r2i
+OUT=gpurun_out/r2k
 mkdir -p $OUT
 export PYTHONUNBUFFERED=1
 : > $OUT/summary.txt
