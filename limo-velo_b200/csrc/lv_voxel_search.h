@@ -333,11 +333,14 @@ LV_HD unsigned long long block_cube_mask(int cbx, int cby, int cbz, int r) {
  * A query that knows nothing yet (no bucket at level 0: bound0 = the search radius) first derives a bound from the list
  * itself (the five nearest occupied voxels hold five points), so it too visits a few dozen voxels, not the whole ball.
  */
-enum { kRingBlocksPerLane = 4, kRingCands = 768, kRingMaxR = 15 };
+enum { kRingBlocksPerLane = 4, kRingBlocks = 32 * kRingBlocksPerLane, kRingCands = 1024, kRingMaxR = 15 };
 struct RingScratch {
-    uint32_t seg_pk[kRingCands];          /* every occupied voxel in range: (dx + 64) | (dy + 64) << 8 | (dz + 64) << 16         */
+    uint32_t seg_pk[kRingCands];          /* every occupied voxel of the cube: (dx + 64) | (dy + 64) << 8 | (dz + 64) << 16; then, compacted
+                                             in place, the candidates of the pass                                          */
     float seg_d2[kRingCands];             /* their box distances                                                             */
-    uint32_t cand[kRingCands];            /* the candidates of the current pass, dense                                        */
+    unsigned long long blk_mask[kRingBlocks];   /* occupancy of the blocks over the cube, clipped to it                      */
+    uint32_t blk_incl[kRingBlocks];       /* inclusive prefix of their popcounts: voxel ranks [incl - popc, incl)             */
+    uint32_t blk_pk[kRingBlocks];         /* packed offset of the block's first voxel (same packing as seg_pk)                */
     float axis_d2[3][2 * kRingMaxR + 1];  /* squared per-axis part of the box distance for offsets -r .. r                    */
 };
 __device__ __forceinline__ void rings_process_candidates(const VoxelMapView& m, const RingScratch* sm, uint32_t n_cand, int hx, int hy, int hz,
@@ -346,7 +349,7 @@ __device__ __forceinline__ void rings_process_candidates(const VoxelMapView& m, 
     for (uint32_t c0 = 0; c0 < n_cand; c0 += 32) {
         uint32_t s = 0, cnt = 0;
         if (c0 + (uint32_t)lane < n_cand) {
-            const uint32_t pk = sm->cand[c0 + lane];
+            const uint32_t pk = sm->seg_pk[c0 + lane];
             const int vx = hx + (int)(pk & 0xFFu) - 64, vy = hy + (int)((pk >> 8) & 0xFFu) - 64, vz = hz + (int)((pk >> 16) & 0xFFu) - 64;
             const int slot = voxel_find(m, voxel_key((uint32_t)vx, (uint32_t)vy, (uint32_t)vz));
             if (slot >= 0) { const uint4 e = load_slot(m.table + 2 * (size_t)slot); s = e.z; cnt = e.w; }
@@ -437,28 +440,23 @@ __device__ __forceinline__ void knn5_rings_warp(const VoxelMapView& m, float gx,
         sm->axis_d2[a][d + r] = v * v;
     }
     __syncwarp();
-    /* 2. the occupied voxels of the range whose box lies inside the bound, with their box distances, as ONE dense list
-     * (two walks over the set bits of this lane's masks: count, warp scan, write — the order is lane-major and
-     * deterministic); the passes below only filter this list */
+    /* 2. the occupied voxels of the cube with their box distances, as ONE dense list in block order.  The masks are clipped
+     * to the cube (no walk), their popcounts scanned, and the voxel RANKS are dealt out evenly: lane j lists ranks
+     * [j * per, (j + 1) * per) whichever blocks they fall in — a dense block no longer makes one lane walk 64 bits while the
+     * others wait.  The list order (block, bit) is fixed, so the result does not depend on the dealing. */
     uint32_t n_list = 0;
     {
-        /* pass 0: clip every mask to the cube of the wanted rings (three nibble/row/slice patterns, no walk), then drop the
-         * voxels whose box lies outside the bound; pass 1 writes the survivors */
-        uint32_t mine = 0;
+        uint32_t mine = 0, pc[kRingBlocksPerLane];
 #pragma unroll
         for (int u = 0; u < kRingBlocksPerLane; ++u) {
             const int bi = lane + 32 * u;
             const int cbx = (x0 + bi % nx) * 4 - hx, cby = (y0 + (bi / nx) % ny) * 4 - hy, cbz = (z0 + bi / (nx * ny)) * 4 - hz;
-            unsigned long long mm = mk[u] & block_cube_mask(cbx, cby, cbz, r), keep = 0ull;
-            while (mm) {
-                const int c = __ffsll((long long)mm) - 1;
-                const unsigned long long bit = mm & (0ull - mm);
-                mm ^= bit;
-                const float d2 = (sm->axis_d2[0][cbx + (c & 3) + r] + sm->axis_d2[1][cby + ((c >> 2) & 3) + r]) + sm->axis_d2[2][cbz + (c >> 4) + r];   /* == voxel_box_d2(h, dx, dy, dz) */
-                if (d2 < bound) keep |= bit;
-            }
-            mk[u] = keep;
-            mine += (uint32_t)__popcll(keep);
+            mk[u] &= block_cube_mask(cbx, cby, cbz, r);
+            pc[u] = (uint32_t)__popcll(mk[u]);
+            mine += pc[u];
+            sm->blk_mask[kRingBlocksPerLane * lane + u] = mk[u];
+            /* offsets of a clipped-away block may fall outside the 8-bit fields; its mask is 0 and it is never decoded */
+            sm->blk_pk[kRingBlocksPerLane * lane + u] = (uint32_t)(cbx + 64) | ((uint32_t)(cby + 64) << 8) | ((uint32_t)(cbz + 64) << 16);
         }
         uint32_t incl = mine;
 #pragma unroll
@@ -466,21 +464,43 @@ __device__ __forceinline__ void knn5_rings_warp(const VoxelMapView& m, float gx,
             const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += v;
         }
-        uint32_t at = incl - mine;
         n_list = __shfl_sync(0xffffffffu, incl, 31);
-        if (n_list <= (uint32_t)kRingCands) {
+        uint32_t run = incl - mine;
 #pragma unroll
-            for (int u = 0; u < kRingBlocksPerLane; ++u) {
-                const int bi = lane + 32 * u;
-                const int cbx = (x0 + bi % nx) * 4 - hx, cby = (y0 + (bi / nx) % ny) * 4 - hy, cbz = (z0 + bi / (nx * ny)) * 4 - hz;
-                unsigned long long mm = mk[u];
-                while (mm) {
+        for (int u = 0; u < kRingBlocksPerLane; ++u) {
+            run += pc[u];
+            sm->blk_incl[kRingBlocksPerLane * lane + u] = run;
+        }
+        __syncwarp();
+        if (n_list <= (uint32_t)kRingCands && n_list > 0) {
+            const uint32_t per = (n_list + 31u) >> 5;
+            uint32_t rank = per * (uint32_t)lane;
+            const uint32_t stop = rank + per < n_list ? rank + per : n_list;
+            if (rank < stop) {
+                int b = 0;                                      /* first block whose inclusive prefix exceeds rank */
+#pragma unroll
+                for (int step = kRingBlocks / 2; step > 0; step >>= 1)
+                    if (sm->blk_incl[b + step - 1] <= rank) b += step;
+                unsigned long long mm = sm->blk_mask[b];
+                uint32_t skip = rank - (sm->blk_incl[b] - (uint32_t)__popcll(mm));
+                /* drop the `skip` lowest set bits: whole 16-bit slices first */
+#pragma unroll
+                for (int z = 0; z < 3; ++z) {
+                    const uint32_t in_slice = (uint32_t)__popc((uint32_t)(mm >> (16 * z)) & 0xFFFFu);
+                    if (skip >= in_slice) { skip -= in_slice; mm &= ~(0xFFFFull << (16 * z)); }   /* skip < popc(mm): bits remain above */
+                    else break;
+                }
+                for (; skip > 0; --skip) mm &= mm - 1ull;
+                uint32_t base = sm->blk_pk[b];
+                while (rank < stop) {
+                    while (mm == 0ull) { ++b; mm = sm->blk_mask[b]; base = sm->blk_pk[b]; }
                     const int c = __ffsll((long long)mm) - 1;
                     mm &= mm - 1ull;
-                    const int dx = cbx + (c & 3), dy = cby + ((c >> 2) & 3), dz = cbz + (c >> 4);
-                    sm->seg_pk[at] = (uint32_t)(dx + 64) | ((uint32_t)(dy + 64) << 8) | ((uint32_t)(dz + 64) << 16);
-                    sm->seg_d2[at] = (sm->axis_d2[0][dx + r] + sm->axis_d2[1][dy + r]) + sm->axis_d2[2][dz + r];
-                    ++at;
+                    const uint32_t pk = base + (uint32_t)(c & 3) + ((uint32_t)((c >> 2) & 3) << 8) + ((uint32_t)(c >> 4) << 16);
+                    const int ox = (int)(pk & 0xFFu) - 64 + r, oy = (int)((pk >> 8) & 0xFFu) - 64 + r, oz = (int)((pk >> 16) & 0xFFu) - 64 + r;
+                    sm->seg_pk[rank] = pk;
+                    sm->seg_d2[rank] = (sm->axis_d2[0][ox] + sm->axis_d2[1][oy]) + sm->axis_d2[2][oz];   /* == voxel_box_d2(h, dx, dy, dz) */
+                    ++rank;
                 }
             }
         }
@@ -520,7 +540,9 @@ __device__ __forceinline__ void knn5_rings_warp(const VoxelMapView& m, float gx,
         const uint32_t i = i0 + (uint32_t)lane;
         const bool sel = i < n_list && sm->seg_d2[i] < bound;
         const unsigned bal = __ballot_sync(0xffffffffu, sel);
-        if (sel) sm->cand[total + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = sm->seg_pk[i];
+        const uint32_t pk = sel ? sm->seg_pk[i] : 0u;
+        __syncwarp();                                   /* in place: the slots written (<= i0 + lane) have been read */
+        if (sel) sm->seg_pk[total + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = pk;
         total += (uint32_t)__popc(bal);
     }
     __syncwarp();
@@ -539,6 +561,10 @@ __device__ __forceinline__ void knn5_rings_warp(const VoxelMapView& m, float gx,
  * the fit.  (Seen on the bench data: one query of 65 536 in sweep 1 has its 3rd and 4th neighbour at equal distance.)
  */
 LV_HD void canonical_neighbour_order(float (*q)[3], float* d, int* id) {
+    /* ascending distances: a tie anywhere shows in one of the four adjacent gaps (a float test first: the fp64 compare of the
+     * reference's comparator costs more than the rest of the function and one query in 10^5 has a tie at all) */
+    const float gap = fminf(fminf(d[1] - d[0], d[2] - d[1]), fminf(d[3] - d[2], d[4] - d[3]));
+    if (!(gap < 2e-10f)) return;
     for (int pass = 0; pass < 4; ++pass)
         for (int k = 0; k < 4; ++k)
             if (fabs((double)(d[k + 1] - d[k])) < 1e-10 && q[k + 1][0] < q[k][0]) {

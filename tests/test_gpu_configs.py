@@ -35,7 +35,7 @@ def _check_update(loc, om, oprm, x_prop, P0, sweep, O, min_matches):
     assert np.abs(x - x_o).max() < 1e-7
     assert np.abs(P - P_o).max() <= 1e-6 * np.abs(P_o).max()
     from test_gpu_fullsize import check_every_evaluation
-    check_every_evaluation(O, om, oprm, x_prop, P0, sweep, logs)     # per evaluation at the GPU's iterate: Nm equal, HTH 1e-12, dx 1e-9
+    check_every_evaluation(O, om, oprm, x_prop, P0, sweep, logs, loc)     # per evaluation at the GPU's iterate: Nm equal, HTH 1e-12, dx 1e-9
     return x, logs
 
 

@@ -19,23 +19,59 @@ def full(lv, O):
                 oprm=bench.oracle_params(O, prm))
 
 
-def check_every_evaluation(O, om, oprm, x_prior, P_prior, sweep, logs):
+def boundary_ties(om, ref, idx):
+    """For the queries `idx`: is the 5th nearest map point exactly as far (fp32 squared distance, the search's arithmetic)
+    as the 6th?  Then WHICH of the two joins the five is decided by the order a search meets them: the reference's
+    max-heap keeps the first one its tree walk visits (ikd_Tree.cpp Search), the restated kd-tree and the voxel search have
+    other walks.  Checked by brute force over the oracle's own map points; about one query in 10^6 is such a tie."""
+    pts = om.points().astype(np.float32)
+    out = []
+    for i in idx:
+        d = pts - ref["g"][i]
+        d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+        s = np.sort(np.partition(d2, 6)[:7])
+        out.append(bool(s[4] == s[5]))
+    return out
+
+
+def check_every_evaluation(O, om, oprm, x_prior, P_prior, sweep, logs, loc=None):
     """The tight form of "the update matches the oracle": evaluation by evaluation, AT THE ITERATE THE GPU MEASURED.
     For evaluation k the GPU's iterate is x_prior (k = 0) or the previous log's x_after.  At that very iterate the oracle's
     measurement (kNN = the reference ikd-Tree where available, plane fit, rows) must give the same Nm and the same normal
     equations up to summation order (1e-12): there is no room for a flipped gate, both sides look at the same fp32 world points.
     The oracle's 23-DoF step from those normal equations must then reproduce the GPU's dx_ and next iterate to 1e-9
-    (SURVEY 8c asks 1e-6 / 1e-5 m).  Nothing is inferred: a per-point disagreement shows up as Nm or HTH."""
+    (SURVEY 8c asks 1e-6 / 1e-5 m).  Nothing is inferred: a per-point disagreement shows up as Nm or HTH.
+
+    The one disagreement the domain itself leaves open is a query whose 5th and 6th nearest map points are EXACTLY equidistant
+    (boundary_ties).  With `loc` given, an evaluation that differs is taken apart per point: every differing query must be
+    such a tie (brute force), there may be at most 4 of them, and with those queries removed from the sweep the two sides must
+    again agree to 1e-12."""
     x_k = np.array(x_prior, dtype=np.float64)
+    ties = 0
     for k, lg in enumerate(logs):
         st, HTH, HTh, nm = om.measure_reduced(x_k, oprm, sweep)
-        assert st == 0 and nm == lg["n_matches"], (k, nm, lg["n_matches"])
-        assert np.abs(HTH - lg["HTH"]).max() <= 1e-12 * np.abs(HTH).max(), (k, np.abs(HTH - lg["HTH"]).max())
+        assert st == 0
+        same = nm == lg["n_matches"] and np.abs(HTH - lg["HTH"]).max() <= 1e-12 * np.abs(HTH).max()
+        if not same:
+            assert loc is not None, (k, nm, lg["n_matches"], np.abs(HTH - lg["HTH"]).max())
+            got, ref = loc.match_all(x_k, sweep), om.match_all(x_k, oprm, sweep)
+            bad = np.nonzero((got["valid"] != ref["valid"]) | (got["plane"] != ref["plane"]).any(1))[0]
+            assert 0 < len(bad) <= 4, (k, bad)
+            assert all(boundary_ties(om, ref, bad)), (k, bad)
+            keep = np.ones(len(sweep), bool)
+            keep[bad] = False
+            st_g, HTH_g, HTh_g, nm_g = loc.measure_reduced(x_k, sweep[keep])
+            st_o, HTH_o, HTh_o, nm_o = om.measure_reduced(x_k, oprm, sweep[keep])
+            assert st_g == st_o == 0 and nm_g == nm_o
+            assert np.abs(HTH_g - HTH_o).max() <= 1e-12 * np.abs(HTH_o).max()
+            HTH, HTh = lg["HTH"], lg["HTh"]        # the step is checked on the normal equations the GPU summed
+            ties += len(bad)
         assert np.abs(HTh - lg["HTh"]).max() <= 1e-12 * max(1.0, np.abs(HTh).max())
         dx, x_new, P_now, Kx, conv = O.update_step(x_prior, P_prior, x_k, oprm, HTH, HTh)
         assert np.abs(dx - lg["dx"]).max() < 1e-9, (k, np.abs(dx - lg["dx"]).max())
         assert np.abs(x_new - lg["x_after"]).max() < 1e-9, (k, np.abs(x_new - lg["x_after"]).max())
         x_k = lg["x_after"]
+    return ties
 
 
 def test_full_size_update_matches_oracle(lv, O, full):
@@ -57,7 +93,7 @@ def test_full_size_update_matches_oracle(lv, O, full):
         # by ~1e-10 (different but equally valid fp64 evaluation orders); SURVEY 8c states 1e-6 for dx_
         assert np.abs(a["dx"] - b["dx"]).max() < (1e-9 if k == 0 else 1e-8), (k, np.abs(a["dx"] - b["dx"]).max())
     assert np.abs(x - x_o).max() < 1e-8
-    check_every_evaluation(O, om, full["oprm"], x_prop, full["P0"], sweep, logs)
+    check_every_evaluation(O, om, full["oprm"], x_prop, full["P0"], sweep, logs, loc)
     err = np.abs(O.boxminus(x, full["truths"][0]))
     assert err[:3].max() < 5e-3 and err[3:6].max() < 5e-4          # centimetre-level localisation
     # per-point parity at full size
@@ -144,7 +180,7 @@ def test_streaming_predict_correct_map_update(lv, O, full):
         st_o, xo, Po, logs_o = om.update_iterated(xo, Po, full["oprm"], sweep)                 # free chain
         assert st == st_s == st_o == 0 and len(logs) == len(logs_s) == len(logs_o)
         # every evaluation, at the GPU's own iterate: same matches, same normal equations, same step (1e-9) — no inference
-        check_every_evaluation(O, om, full["oprm"], x_prior, P_prior, sweep, logs)
+        check_every_evaluation(O, om, full["oprm"], x_prior, P_prior, sweep, logs, loc)
         # the two free-running oracle chains are weaker statements (their iterates drift by ~1e-9, which re-rounds ~0.1 % of the fp32
         # world points and now and then flips one hard gate of 58 000): unconditional bars, no flip detection
         for a, b, c in zip(logs, logs_s, logs_o):
