@@ -102,7 +102,14 @@ struct MapGrid {
 };
 
 LV_HD int cell_coord(float v, float ds) { return (int)floorf(fdiv(v, ds)); }   /* ikd_Tree.cpp:493 */
-LV_HD int floor_div(int a, int k) { return a >= 0 ? a / k : -((-a + k - 1) / k); }
+/* floor(a / k).  k is 1, 2 or 3 on every map this library builds (MapGrid::k): those cases cost a shift or a
+ * multiply-high instead of a runtime integer division (three of them per query in every search kernel). */
+LV_HD int floor_div(int a, int k) {
+    if (k == 1) return a;
+    if (k == 2) return a >> 1;                                   /* arithmetic shift: floor for negative a too */
+    if (k == 3) return a >= 0 ? a / 3 : -((-a + 2) / 3);
+    return a >= 0 ? a / k : -((-a + k - 1) / k);
+}
 /* biased (non-negative, 21-bit) voxel coordinate of cell coordinate c */
 LV_HD uint32_t voxel_of_cell(int c, int k) {
     int v = floor_div(c, k) + LV_KEY_BIAS;

@@ -343,13 +343,13 @@ struct RingScratch {
     uint32_t blk_pk[kRingBlocks];         /* packed offset of the block's first voxel (same packing as seg_pk)                */
     float axis_d2[3][2 * kRingMaxR + 1];  /* squared per-axis part of the box distance for offsets -r .. r                    */
 };
-__device__ __forceinline__ void rings_process_candidates(const VoxelMapView& m, const RingScratch* sm, uint32_t n_cand, int hx, int hy, int hz,
+__device__ __forceinline__ void rings_process_candidates(const VoxelMapView& m, const uint32_t* cand, uint32_t n_cand, int hx, int hy, int hz,
                                                          float gx, float gy, float gz, Top5& loc) {
     const int lane = (int)(threadIdx.x & 31u);
     for (uint32_t c0 = 0; c0 < n_cand; c0 += 32) {
         uint32_t s = 0, cnt = 0;
         if (c0 + (uint32_t)lane < n_cand) {
-            const uint32_t pk = sm->seg_pk[c0 + lane];
+            const uint32_t pk = cand[c0 + lane];
             const int vx = hx + (int)(pk & 0xFFu) - 64, vy = hy + (int)((pk >> 8) & 0xFFu) - 64, vz = hz + (int)((pk >> 16) & 0xFFu) - 64;
             const int slot = voxel_find(m, voxel_key((uint32_t)vx, (uint32_t)vy, (uint32_t)vz));
             if (slot >= 0) { const uint4 e = load_slot(m.table + 2 * (size_t)slot); s = e.z; cnt = e.w; }
@@ -426,18 +426,41 @@ __device__ __forceinline__ void knn5_rings_warp(const VoxelMapView& m, float gx,
     }
     /* 1. block masks */
     unsigned long long mk[kRingBlocksPerLane];
+    int cb[kRingBlocksPerLane][3];       /* voxel offset of each block's first voxel from the home voxel */
+    {
+        /* block index -> (ix, iy, iz) with two reciprocal multiplies (exact for indices < 2^16 / n; the index is < 128):
+         * runtime integer divisions were a third of this kernel's instructions */
+        const uint32_t inv_nx = (65536u + (uint32_t)nx - 1u) / (uint32_t)nx, inv_ny = (65536u + (uint32_t)ny - 1u) / (uint32_t)ny;
+        /* the first probe of all four lookups in flight together (a probe is a dependent round trip; the table is sparse,
+         * so the first slot nearly always decides); block_find() finishes the rare collision */
+        uint64_t key[kRingBlocksPerLane];
+        uint4 e[kRingBlocksPerLane];
 #pragma unroll
-    for (int u = 0; u < kRingBlocksPerLane; ++u) {
-        const int bi = lane + 32 * u;
-        mk[u] = bi < nb ? block_find(m, voxel_key((uint32_t)(x0 + bi % nx), (uint32_t)(y0 + (bi / nx) % ny), (uint32_t)(z0 + bi / (nx * ny)))) : 0ull;
+        for (int u = 0; u < kRingBlocksPerLane; ++u) {
+            const uint32_t bi = (uint32_t)(lane + 32 * u);
+            const uint32_t t = (bi * inv_nx) >> 16, ix = bi - t * (uint32_t)nx;
+            const uint32_t iz = (t * inv_ny) >> 16, iy = t - iz * (uint32_t)ny;
+            cb[u][0] = (x0 + (int)ix) * 4 - hx; cb[u][1] = (y0 + (int)iy) * 4 - hy; cb[u][2] = (z0 + (int)iz) * 4 - hz;
+            key[u] = voxel_key((uint32_t)(x0 + (int)ix), (uint32_t)(y0 + (int)iy), (uint32_t)(z0 + (int)iz));
+            e[u] = (int)bi < nb ? load_slot(m.btable + (size_t)((voxel_hash(key[u]) * 0x9E3779B1u) & m.bmask)) : make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < kRingBlocksPerLane; ++u) {
+            if (e[u].x == (uint32_t)key[u] && e[u].y == (uint32_t)(key[u] >> 32)) mk[u] = (uint64_t)e[u].z | ((uint64_t)e[u].w << 32);
+            else if ((e[u].x & e[u].y) == 0xFFFFFFFFu) mk[u] = 0ull;
+            else mk[u] = block_find(m, key[u]);
+        }
     }
     /* per-axis parts of the box distance (voxel_box_d2, one table entry per offset) */
-    for (int e = lane; e < 3 * (2 * r + 1); e += 32) {
-        const int a = e / (2 * r + 1), d = e - a * (2 * r + 1) - r;
-        float v = d < 0 ? h.lo[a] + (float)(-d - 1) * h.edge : (d > 0 ? h.hi[a] + (float)(d - 1) * h.edge : 0.f);
-        v = d == 0 ? 0.f : v - h.slack * (float)(d < 0 ? -d : d);
-        v = v > 0.f ? v : 0.f;
-        sm->axis_d2[a][d + r] = v * v;
+    if (lane <= 2 * r) {                  /* 2 r + 1 <= 31 offsets per axis: one lane each */
+        const int d = lane - r;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            float v = d < 0 ? h.lo[a] + (float)(-d - 1) * h.edge : (d > 0 ? h.hi[a] + (float)(d - 1) * h.edge : 0.f);
+            v = d == 0 ? 0.f : v - h.slack * (float)(d < 0 ? -d : d);
+            v = v > 0.f ? v : 0.f;
+            sm->axis_d2[a][lane] = v * v;
+        }
     }
     __syncwarp();
     /* 2. the occupied voxels of the cube with their box distances, as ONE dense list in block order.  The masks are clipped
@@ -449,8 +472,7 @@ __device__ __forceinline__ void knn5_rings_warp(const VoxelMapView& m, float gx,
         uint32_t mine = 0, pc[kRingBlocksPerLane];
 #pragma unroll
         for (int u = 0; u < kRingBlocksPerLane; ++u) {
-            const int bi = lane + 32 * u;
-            const int cbx = (x0 + bi % nx) * 4 - hx, cby = (y0 + (bi / nx) % ny) * 4 - hy, cbz = (z0 + bi / (nx * ny)) * 4 - hz;
+            const int cbx = cb[u][0], cby = cb[u][1], cbz = cb[u][2];
             mk[u] &= block_cube_mask(cbx, cby, cbz, r);
             pc[u] = (uint32_t)__popcll(mk[u]);
             mine += pc[u];
@@ -520,6 +542,8 @@ __device__ __forceinline__ void knn5_rings_warp(const VoxelMapView& m, float gx,
      * within 2 m.  The list tells it better: every listed voxel holds at least one point, so the five voxels with the smallest
      * box distances hold five points no farther than (5th smallest box distance + the voxel diagonal) — an upper bound of the
      * 5th neighbour distance, and the only voxels that can matter are those whose box lies inside it. */
+    Top5 loc;
+    float first_d2 = -1.f;                /* voxels with a box distance <= first_d2 are searched first (blind queries only) */
     if (!(bound0 < max_d2)) {
         Top5 sel;
         top5_init(sel, bound);
@@ -530,15 +554,40 @@ __device__ __forceinline__ void knn5_rings_warp(const VoxelMapView& m, float gx,
             const float reach = (fsqrt(s5.d4) + h.slack * (float)(r + 1) + 1.7320509f * h.edge) * 1.0001f;
             const float b1 = reach * reach;
             bound = b1 < bound ? b1 : bound;
+            /* ... and the points of those nearest voxels give the real thing: search them first, take the 5th distance found
+             * as the bound for the rest (their list lives in blk_pk, free since the walk) */
+            uint32_t n_first = 0;
+            for (uint32_t i0 = 0; i0 < n_list && n_first <= (uint32_t)kRingBlocks; i0 += 32) {
+                const uint32_t i = i0 + (uint32_t)lane;
+                const bool pick = i < n_list && sm->seg_d2[i] <= s5.d4;
+                const unsigned bal = __ballot_sync(0xffffffffu, pick);
+                const uint32_t at = n_first + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+                if (pick && at < (uint32_t)kRingBlocks) sm->blk_pk[at] = sm->seg_pk[i];
+                n_first += (uint32_t)__popc(bal);
+            }
+            __syncwarp();
+            if (n_first <= (uint32_t)kRingBlocks) {
+                Top5 part, t5;
+                top5_init(part, bound);
+                rings_process_candidates(m, sm->blk_pk, n_first, hx, hy, hz, gx, gy, gz, part);
+                GroupWarp::merge(part, bound, t5);
+                if (t5.i4 >= 0) {
+                    const float b2 = nextafterf(t5.d4, INFINITY);
+                    bound = b2 < bound ? b2 : bound;
+                }
+                first_d2 = s5.d4;
+                top5_init(loc, bound);
+                if (lane == 0) loc = t5;                    /* the rest joins what the first voxels gave */
+            }
         }
     }
-    Top5 loc;
-    top5_init(loc, bound);
-    /* the candidates: the listed voxels inside the bound, in list order */
+    if (first_d2 < 0.f) top5_init(loc, bound);
+    /* the candidates: the listed voxels inside the bound (and not searched yet), in list order */
     uint32_t total = 0;
     for (uint32_t i0 = 0; i0 < n_list; i0 += 32) {
         const uint32_t i = i0 + (uint32_t)lane;
-        const bool sel = i < n_list && sm->seg_d2[i] < bound;
+        const float d2 = i < n_list ? sm->seg_d2[i] : INFINITY;
+        const bool sel = d2 < bound && d2 > first_d2;
         const unsigned bal = __ballot_sync(0xffffffffu, sel);
         const uint32_t pk = sel ? sm->seg_pk[i] : 0u;
         __syncwarp();                                   /* in place: the slots written (<= i0 + lane) have been read */
@@ -547,7 +596,7 @@ __device__ __forceinline__ void knn5_rings_warp(const VoxelMapView& m, float gx,
     }
     __syncwarp();
     /* 3. probe + scan, one merge */
-    rings_process_candidates(m, sm, total, hx, hy, hz, gx, gy, gz, loc);
+    rings_process_candidates(m, sm->seg_pk, total, hx, hy, hz, gx, gy, gz, loc);
     if (region_d2) *region_d2 = bound;     /* every voxel whose box lies inside the bound has been visited */
     GroupWarp::merge(loc, bound, out);
 }
