@@ -493,17 +493,22 @@ def run_native(args, rank, local_rank, world_size):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         m_launches = max(1, prof["measure_launches"])
         m_ms = prof["measure_ms"] / m_launches
-        k_ms = {"lv_search_kernel": prof["search_ms"] / m_launches, "lv_search_upper_kernel": prof["search_upper_ms"] / m_launches,
+        k_ms = {"lv_search_kernel": prof["search_ms"] / m_launches, "lv_search_rings_kernel": prof["search_upper_ms"] / m_launches,
                 "lv_fit_kernel": prof["fit_ms"] / m_launches, "lv_ieskf_step_kernel": prof["solve_ms"] / max(1, prof["solve_launches"])}
         # The roofline kernel is the search: the largest of the per-point kernels (SURVEY 8d's unit is the point).
         # lv_ieskf_step_kernel takes about as long per evaluation but moves no per-point bytes: it is ~12 us of
         # dependent fp64 23x23 algebra in one block; its time is listed in kernel_ms.
         dominant = "lv_search_kernel"
         achieved = ALGO_BYTES_PER_POINT * n / (k_ms[dominant] * 1e-3) / 1e9 if k_ms[dominant] > 0 else 0.0
-        traffic = None
+        traffic, traffic_src = None, None
         try:                                                        # dram bytes per launch from the committed ncu --set full capture
+            if cfg != "cfg1" or args.sort_queries or args.voxel:
+                raise LookupError("the capture is of the default cfg1 run")
             tr = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))
-            traffic = next(v["dram_bytes_per_launch"] for k, v in tr.items() if k.startswith(dominant))
+            # the first evaluation's search (every query: the launch the algorithmic bytes are counted for)
+            name = next(k for k in tr if k.startswith(dominant) and k.rstrip(">").endswith("0"))
+            traffic = tr[name]["dram_bytes_per_launch"]
+            traffic_src = "profiles/kernel_traffic.json [%s], from the committed ncu --set full capture of `bench.py --steps 2` (cfg1); not re-measured by this run" % name
         except Exception:
             pass
         cpu = None
@@ -531,7 +536,7 @@ def run_native(args, rank, local_rank, world_size):
                           "solve_avg": prof["solve_ms"] / max(1, prof["solve_launches"]),
                           "solve_launches": prof["solve_launches"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                         "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak_gbs, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "kernel": dominant, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_POINT * n},
             "cpu_baseline": cpu,
             "per_sweep": per_sweep,
