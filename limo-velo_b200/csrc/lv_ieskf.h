@@ -140,10 +140,57 @@ struct ExecBlock {
             if (tid == 0) { *s_piv = r; *s_pivval = M[r * w + k]; }
         }
     }
-    /* Gauss-Jordan with partial pivoting on the 12 x 25 system [A | B] of the gain, inside warp 0: lane j holds
-     * column j in 12 registers, lane k picks the pivot of step k, the multipliers M[i][k] travel by shuffle.
-     * Same pivots and the same operations on the same values as gj_solve(), so the same result; 12 barrier-free
-     * steps instead of 36 block barriers.  On return M[k][12..24] = (A^-1 B)[k]. */
+    /* Gauss-Jordan with partial pivoting on the 12 x 25 system [A | B] of the gain, inside warp 0, lane j owning column j.
+     * Same pivots and the same operations on the same values as gj_solve(), so the same result; 12 barrier-free steps
+     * instead of 36 block barriers.  On return M[k][12..24] = (A^-1 B)[k].
+     * Two forms.  The default holds each column in 12 registers with every step unrolled: 4 100 straight-line instructions
+     * that warp 0 runs through once per evaluation in 8 650 cycles (clock64, tools/step_timing.py).  -DLV_GJ_SMEM keeps the
+     * matrix in shared memory and rolls the 12 steps (150 instructions of code); it was written because ncu shows this kernel
+     * stalled on instruction fetch more than on anything but its barriers (no_instruction 10.7 per issue, 60 % instruction-
+     * cache hit rate) — and measured at 16 150 cycles: the shared-memory round trips cost more than the fetches. */
+#if defined(LV_GJ_SMEM)
+    __device__ __noinline__ void solve_12x25(double* M, int32_t*, double*) {
+        if (tid < 32) {
+            const int lane = tid;
+            const bool act = lane < 25;
+            if (lane == 0) LV_TK(48);
+#pragma unroll 1
+            for (int k = 0; k < 12; ++k) {
+                /* every lane finds the pivot of column k itself (broadcast reads): row >= k with the largest |value|, lowest on ties */
+                int p = k;
+                double best = fabs(M[k * 25 + k]);
+#pragma unroll 1
+                for (int i = k + 1; i < 12; ++i) {
+                    const double v = fabs(M[i * 25 + k]);
+                    if (v > best) { best = v; p = i; }
+                }
+                const double ipv = 1.0 / M[p * 25 + k];
+                __syncwarp();                            /* column k is about to change under the readers */
+                double ck = 0.0;                         /* the scaled pivot row, this lane's column */
+                if (act) {
+                    const double a = M[k * 25 + lane], b = M[p * 25 + lane];
+                    if (p != k) M[p * 25 + lane] = a;
+                    ck = b * ipv;
+                    M[k * 25 + lane] = ck;
+                }
+                __syncwarp();
+                double m[12];                            /* the multipliers: column k after the swap */
+#pragma unroll
+                for (int i = 0; i < 12; ++i) m[i] = M[i * 25 + k];
+                __syncwarp();
+                if (act) {
+#pragma unroll
+                    for (int i = 0; i < 12; ++i)
+                        if (i != k) M[i * 25 + lane] -= m[i] * ck;
+                }
+                __syncwarp();
+            }
+            if (lane == 0) { LV_TK(49); LV_TK(52); }
+        }
+        __syncthreads();
+    }
+#else
+    /* lane j holds column j in 12 registers, lane k picks the pivot of step k, the multipliers M[i][k] travel by shuffle */
     __device__ __noinline__ void solve_12x25(double* M, int32_t*, double*) {
         if (tid < 32) {
             const int lane = tid;
@@ -186,6 +233,7 @@ struct ExecBlock {
         }
         __syncthreads();
     }
+#endif
 };
 #endif
 

@@ -152,16 +152,16 @@ __global__ void __launch_bounds__(LV_SEARCH_THREADS) lv_search_kernel(const Meas
         qi = have ? listed : 0;
     }
     float g[3] = {0.f, 0.f, 0.f};
-    uint32_t bs = 0, bc = 0;
+    uint32_t bs = 0, bc = 0, vox[3] = {0u, 0u, 0u};
     int st = 0;                       /* 0 no query / not finite, 1 bucket, 2 no level-0 slot */
     if (have) {
         rt_apply(T, jb.xyz[3 * qi], jb.xyz[3 * qi + 1], jb.xyz[3 * qi + 2], g);   /* Mapper.cpp:51 */
         const bool finite = (fabsf(g[0]) < 1e9f) && (fabsf(g[1]) < 1e9f) && (fabsf(g[2]) < 1e9f);
-        if (finite) st = level0_probe(a.map, g[0], g[1], g[2], &bs, &bc) >= 0 ? 1 : 2;
+        if (finite) st = level0_probe(a.map, g[0], g[1], g[2], &bs, &bc, vox) >= 0 ? 1 : 2;
     }
     Top5 t;
     float region = 0.f;
-    const bool settled = level0_scan<Grp>(a.map, g[0], g[1], g[2], a.max_d2, bs, bc, st == 1, t, &region);
+    const bool settled = level0_scan<Grp>(a.map, g[0], g[1], g[2], a.max_d2, bs, bc, st == 1, t, &region, vox);
     if (have && (threadIdx.x & (G - 1)) == 0) {
         store_neighbours(a, qi, t);
         const bool hard = st == 2 || (st == 1 && !settled);

@@ -107,8 +107,7 @@ LV_HD int cell_coord(float v, float ds) { return (int)floorf(fdiv(v, ds)); }   /
 LV_HD int floor_div(int a, int k) {
     if (k == 1) return a;
     if (k == 2) return a >> 1;                                   /* arithmetic shift: floor for negative a too */
-    if (k == 3) return a >= 0 ? a / 3 : -((-a + 2) / 3);
-    return a >= 0 ? a / k : -((-a + k - 1) / k);
+    return a >= 0 ? a / 3 : -((-a + 2) / 3);                     /* k == 3 (map_alloc clamps k to 1..3) */
 }
 /* biased (non-negative, 21-bit) voxel coordinate of cell coordinate c */
 LV_HD uint32_t voxel_of_cell(int c, int k) {

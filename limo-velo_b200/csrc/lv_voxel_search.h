@@ -217,8 +217,9 @@ LV_HD float voxel_box_d2(const HomeGeom& h, int dx, int dy, int dz) {
  *                  query with a bucket; inactive groups only take part in the collectives.
  * Ids are positions in the arena.
  */
-LV_HD int level0_probe(const VoxelMapView& m, float gx, float gy, float gz, uint32_t* bstart, uint32_t* bcount) {
+LV_HD int level0_probe(const VoxelMapView& m, float gx, float gy, float gz, uint32_t* bstart, uint32_t* bcount, uint32_t* vox = nullptr) {
     const uint32_t bx0 = voxel_coord(m.grid, gx), by0 = voxel_coord(m.grid, gy), bz0 = voxel_coord(m.grid, gz);
+    if (vox) { vox[0] = bx0; vox[1] = by0; vox[2] = bz0; }    /* three IEEE divisions: callers hand them on to level0_scan */
     const int slot = voxel_find(m, voxel_key(bx0, by0, bz0));
     *bstart = 0;
     *bcount = 0;
@@ -235,7 +236,7 @@ LV_HD float level0_certified(const VoxelMapView& m, float gx, float gy, float gz
 
 template <class Grp>
 LV_HD bool level0_scan(const VoxelMapView& m, float gx, float gy, float gz, float max_d2, uint32_t bstart, uint32_t bcount,
-                       bool active, Top5& out, float* region_d2 = nullptr) {
+                       bool active, Top5& out, float* region_d2 = nullptr, const uint32_t* vox = nullptr) {
     Top5 loc;
     top5_init(loc, max_d2);
     if (active) {
@@ -257,7 +258,7 @@ LV_HD bool level0_scan(const VoxelMapView& m, float gx, float gy, float gz, floa
     }
     Grp::merge(loc, max_d2, out);
     if (!active) return false;
-    const float cert = level0_certified(m, gx, gy, gz);
+    const float cert = vox ? certified_d2(home_geom(m.grid, vox[0], vox[1], vox[2], gx, gy, gz)) : level0_certified(m, gx, gy, gz);
     if (region_d2) *region_d2 = cert;     /* every map point outside the bucket is at least this far (squared) */
     return out.d4 <= cert;                /* out.d4 <= max_d2 always */
 }
