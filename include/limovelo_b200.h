@@ -249,7 +249,8 @@ lv_status lv_temporal_downsample(lv_handle h, const float* xyz, int64_t n, int32
                                  float* xyz_out, int32_t* idx_out, int64_t* n_out);
 /* Compensator::downsample -> voxelgrid_downsample (src/Modules/Compensator.cpp:115-118,148-163): pcl::VoxelGrid with
  * leaf downsample_prec: one centroid per occupied leaf, leaves in ascending PCL cell index.  xyz_out needs room for
- * n points.  LV_ERR_ARG when the leaf is too small for the extent (PCL refuses and returns the input).      */
+ * n points.  When the leaf is too small for the extent (cell index overflow) PCL warns and returns the input: so does
+ * this (n_out = n, LV_OK, the warning in lv_last_error()).                                                          */
 lv_status lv_voxelgrid_downsample(lv_handle h, const float* xyz, int64_t n, float downsample_prec, float* xyz_out,
                                   int64_t* n_out);
 /* the same on device-resident buffers (d_xyz_out must not alias d_xyz)                                    */

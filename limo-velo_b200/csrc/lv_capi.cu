@@ -899,7 +899,15 @@ lv_status lv_voxelgrid_downsample_device(lv_handle h, const float* d_xyz, int64_
     LV_CUDA(launch_voxelgrid(h->ds, d_xyz, n, leaf, d_xyz_out, h->stream, &launches));
     h->prof.total_launches += launches;
     LV_CUDA(cudaStreamSynchronize(h->stream));
-    if (h->ds.h_count[1]) { set_error("voxel grid: leaf size too small for the extent of the cloud (cell index overflows)"); return LV_ERR_ARG; }
+    if (h->ds.h_count[1]) {
+        /* pcl::VoxelGrid::applyFilter warns "Leaf size is too small for the input dataset. Integer indices would overflow."
+         * and hands the input on unchanged; Compensator::voxelgrid_downsample carries on with it.  Same here. */
+        set_error("voxel grid: leaf size too small for the extent of the cloud (cell index overflows): input passed through");
+        if (d_xyz_out != d_xyz) LV_CUDA(cudaMemcpyAsync(d_xyz_out, d_xyz, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
+        LV_CUDA(cudaStreamSynchronize(h->stream));
+        *n_out = n;
+        return LV_OK;
+    }
     *n_out = h->ds.h_count[0];
     return LV_OK;
 }

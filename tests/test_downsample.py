@@ -43,6 +43,7 @@ def test_voxelgrid_downsample_matches_oracle(lv, O, scene_xaloc, scene_kitti, le
             ref = O.voxelgrid_downsample(xyz, leaf)
             assert got.shape == ref.shape
             assert (got == ref).all()
-        with pytest.raises(RuntimeError):
-            loc.voxelgrid_downsample(sc.sweep, 1e-5)
+        # PCL warns and hands the input on when the cell index would overflow (voxel_grid.hpp applyFilter); so does the library
+        passed = loc.voxelgrid_downsample(sc.sweep, 1e-5)
+        assert passed.shape == sc.sweep.shape and (passed == sc.sweep).all()
         loc.close()
