@@ -174,6 +174,71 @@ __global__ void __launch_bounds__(LV_SEARCH_THREADS) lv_search_kernel(const Meas
     LV_TL_END(2);
 }
 
+/*
+ * K1c — search, level 0, query-per-lane prologue + 8-lane scans (LV_SEARCH_GROUP=32).  In K1 every instruction of a query's
+ * prologue (world transform, three IEEE divisions for the voxel coordinate, hash, probe, face distances) is issued for a warp
+ * that holds only FOUR queries: ncu puts 40 % of K1's instructions there.  Here a warp holds 32 queries: each lane does the
+ * prologue of its own query (32 probes in flight per warp), then the warp walks its queries four at a time — the owner
+ * lanes hand (point, bucket, certified radius) to the 8-lane groups by shuffle, which scan and merge exactly as K1 does.
+ * Same candidates, same merge, same answers; an eighth of the prologue instructions.
+ */
+#define LV_COOP_THREADS 64
+template <bool LIST>
+__global__ void __launch_bounds__(LV_COOP_THREADS) lv_search_coop_kernel(const MeasureArgs a) {
+    typedef GroupLanes<8> Grp;
+    LV_TL_SCHED();
+    pdl_wait();
+    pdl_trigger();
+    LV_TL_WORK(a.ctrl, 2);
+    const int done = a.ctrl->done;
+    const Rt32 T = a.ctrl->frame.lidar_to_world;
+    const JobView jb = job_view(a);
+    const int n_redo = LIST ? (int)a.hard_count[2] : 0;
+    const int slot = (int)(blockIdx.x * LV_COOP_THREADS + threadIdx.x);
+    const int listed = LIST ? (int)a.redo_list[slot < (int)a.n ? slot : 0] : 0;
+    if (done) return;
+    if (LIST && (int)(blockIdx.x * LV_COOP_THREADS) >= n_redo) return;
+    const bool have = LIST ? slot < n_redo : slot < jb.n;
+    const int qi = have ? (LIST ? listed : slot) : 0;
+    /* 1. one query per lane */
+    float g[3] = {0.f, 0.f, 0.f}, cert = 0.f;
+    uint32_t bs = 0, bc = 0, vox[3] = {0u, 0u, 0u};
+    int st = 0;                       /* 0 no query / not finite, 1 bucket, 2 no level-0 slot */
+    if (have) {
+        rt_apply(T, jb.xyz[3 * qi], jb.xyz[3 * qi + 1], jb.xyz[3 * qi + 2], g);   /* Mapper.cpp:51 */
+        const bool finite = (fabsf(g[0]) < 1e9f) && (fabsf(g[1]) < 1e9f) && (fabsf(g[2]) < 1e9f);
+        if (finite) st = level0_probe(a.map, g[0], g[1], g[2], &bs, &bc, vox) >= 0 ? 1 : 2;
+        if (st == 1) cert = certified_d2(home_geom(a.map.grid, vox[0], vox[1], vox[2], g[0], g[1], g[2]));
+    }
+    /* 2. four queries at a time, 8 lanes each */
+    const int lane = (int)(threadIdx.x & 31u);
+#pragma unroll 1
+    for (int r = 0; r < 8; ++r) {
+        const int src = 4 * r + (lane >> 3);
+        const int st_r = __shfl_sync(0xffffffffu, st, src);
+        const bool have_r = __shfl_sync(0xffffffffu, have ? 1 : 0, src) != 0;
+        if (!__ballot_sync(0xffffffffu, have_r)) break;           /* slots ascend with the lane: nothing further either */
+        const float gx = __shfl_sync(0xffffffffu, g[0], src), gy = __shfl_sync(0xffffffffu, g[1], src), gz = __shfl_sync(0xffffffffu, g[2], src);
+        const uint32_t bs_r = __shfl_sync(0xffffffffu, bs, src), bc_r = __shfl_sync(0xffffffffu, bc, src);
+        const float cert_r = __shfl_sync(0xffffffffu, cert, src);
+        const int qi_r = __shfl_sync(0xffffffffu, qi, src);
+        Top5 t;
+        float region = 0.f;
+        const bool settled = level0_scan<Grp>(a.map, gx, gy, gz, a.max_d2, bs_r, bc_r, st_r == 1, t, &region, nullptr, &cert_r);
+        if (have_r && (lane & 7) == 0) {
+            store_neighbours(a, qi_r, t);
+            const bool hard = st_r == 2 || (st_r == 1 && !settled);
+            const float gq[3] = {gx, gy, gz};
+            store_ref(a, qi_r, gq, (st_r == 1 && settled) ? outsider_bound(t.d5, region) : 0.f);
+            if (hard) {
+                const uint32_t b = blockIdx.x % kHardBuckets;
+                a.hard_list[(size_t)b * a.hard_seg + atomicAdd(a.hard_count + 4 + b, 1u)] = (uint32_t)qi_r;
+            }
+        }
+    }
+    LV_TL_END(2);
+}
+
 /* ---- bulk copies into shared memory (TMA engine, 1-D form) and the mbarrier they complete on ---------------- */
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -805,30 +870,31 @@ int measure_grid(int n) {
 
 void measure_init() { init_pairs(); }
 
-static int search_group() {   /* lanes per query in K1; LV_SEARCH_GROUP overrides for tuning runs */
-    static int group = 0;
-    if (!group) {
-        const char* e = getenv("LV_SEARCH_GROUP");
-        group = e ? atoi(e) : LV_GROUP;
-        if (group != 1 && group != 8) group = LV_GROUP;
-    }
+static int search_group() {   /* K1 variant: lanes per query (1, 8) or 32 = lv_search_coop_kernel; LV_SEARCH_GROUP overrides for tuning runs and tests
+                               * (read at every direct launch and when a handle's graph is built, so a test can switch it between handles) */
+    const char* e = getenv("LV_SEARCH_GROUP");
+    int group = e ? atoi(e) : LV_GROUP;
+    if (group != 1 && group != 8 && group != 32) group = LV_GROUP;
     return group;
 }
+static int search_block(int group) { return group == 32 ? LV_COOP_THREADS : LV_SEARCH_THREADS; }
 static int search_grid(const MeasureArgs& a, int group) {
-    const int sgrid = (int)(((int64_t)a.n * group + LV_SEARCH_THREADS - 1) / LV_SEARCH_THREADS);
+    const int sgrid = group == 32 ? (int)(((int64_t)a.n + LV_COOP_THREADS - 1) / LV_COOP_THREADS)
+                                  : (int)(((int64_t)a.n * group + LV_SEARCH_THREADS - 1) / LV_SEARCH_THREADS);
     return sgrid < 1 ? 1 : sgrid;
 }
 template <bool LIST>
 static const void* search_kernel_ptr(int group) {
-    return group == 1 ? (const void*)lv_search_kernel<1, LIST> : (const void*)lv_search_kernel<8, LIST>;
+    return group == 1 ? (const void*)lv_search_kernel<1, LIST>
+                      : (group == 32 ? (const void*)lv_search_coop_kernel<LIST> : (const void*)lv_search_kernel<8, LIST>);
 }
 void measure_kernel_shapes(const MeasureArgs& a, int grid, MeasureKernelShape out[kMeasureKernels]) {
     const int group = search_group();
     out[0].func = search_kernel_ptr<false>(group);
-    out[0].grid = (unsigned)search_grid(a, group); out[0].block = LV_SEARCH_THREADS;
+    out[0].grid = (unsigned)search_grid(a, group); out[0].block = (unsigned)search_block(group);
     out[1].func = (const void*)lv_search_rings_kernel; out[1].grid = kRingsGrid; out[1].block = 128;
     out[2].func = (const void*)lv_fit_kernel; out[2].grid = (unsigned)(grid + (a.prep ? 1 : 0)); out[2].block = kMeasureThreads;
-    out[3].func = search_kernel_ptr<true>(group); out[3].grid = out[0].grid; out[3].block = LV_SEARCH_THREADS;
+    out[3].func = search_kernel_ptr<true>(group); out[3].grid = out[0].grid; out[3].block = out[0].block;
     out[4].func = (const void*)lv_reuse_kernel; out[4].grid = (unsigned)((a.n + 127) / 128 > 0 ? (a.n + 127) / 128 : 1); out[4].block = 128;
 }
 
@@ -851,6 +917,7 @@ template <bool LIST>
 static void launch_search(const MeasureArgs& a, int group, int sgrid, cudaStream_t st, bool pdl) {
     switch (group) {
         case 1: launch_k(lv_search_kernel<1, LIST>, sgrid, LV_SEARCH_THREADS, st, pdl, a); break;
+        case 32: launch_k(lv_search_coop_kernel<LIST>, sgrid, LV_COOP_THREADS, st, pdl, a); break;
         default: launch_k(lv_search_kernel<8, LIST>, sgrid, LV_SEARCH_THREADS, st, pdl, a); break;
     }
 }

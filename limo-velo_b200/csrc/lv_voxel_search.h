@@ -236,7 +236,7 @@ LV_HD float level0_certified(const VoxelMapView& m, float gx, float gy, float gz
 
 template <class Grp>
 LV_HD bool level0_scan(const VoxelMapView& m, float gx, float gy, float gz, float max_d2, uint32_t bstart, uint32_t bcount,
-                       bool active, Top5& out, float* region_d2 = nullptr, const uint32_t* vox = nullptr) {
+                       bool active, Top5& out, float* region_d2 = nullptr, const uint32_t* vox = nullptr, const float* cert_d2 = nullptr) {
     Top5 loc;
     top5_init(loc, max_d2);
     if (active) {
@@ -258,7 +258,9 @@ LV_HD bool level0_scan(const VoxelMapView& m, float gx, float gy, float gz, floa
     }
     Grp::merge(loc, max_d2, out);
     if (!active) return false;
-    const float cert = vox ? certified_d2(home_geom(m.grid, vox[0], vox[1], vox[2], gx, gy, gz)) : level0_certified(m, gx, gy, gz);
+    /* cert_d2: the caller computed certified_d2() already (lv_search_coop_kernel does it once per query, not once per lane group) */
+    const float cert = cert_d2 ? *cert_d2
+                               : (vox ? certified_d2(home_geom(m.grid, vox[0], vox[1], vox[2], gx, gy, gz)) : level0_certified(m, gx, gy, gz));
     if (region_d2) *region_d2 = cert;     /* every map point outside the bucket is at least this far (squared) */
     return out.d4 <= cert;                /* out.d4 <= max_d2 always */
 }

@@ -129,10 +129,10 @@ def test_neighbour_reuse_and_graph_replay_change_nothing(lv, full, monkeypatch):
     replayed as a CUDA graph, its kernels overlap their launches (programmatic dependent launch): none of it may
     change a single bit of the update"""
     def run(env):
-        for k in ("LV_NO_REUSE", "LV_NO_GRAPH", "LV_NO_PDL"):
+        for k in ("LV_NO_REUSE", "LV_NO_GRAPH", "LV_NO_PDL", "LV_SEARCH_GROUP"):
             monkeypatch.delenv(k, raising=False)
         for k in env:
-            monkeypatch.setenv(k, "1")
+            monkeypatch.setenv(*(k.split("=") if "=" in k else (k, "1")))
         loc = lv.Localizer(full["prm"])                 # the switches are read by lv_create
         loc.map_build(full["map"])
         out = []
@@ -143,7 +143,10 @@ def test_neighbour_reuse_and_graph_replay_change_nothing(lv, full, monkeypatch):
         loc.close()
         return out
     base = run(["LV_NO_REUSE", "LV_NO_GRAPH", "LV_NO_PDL"])
-    for env in ([], ["LV_NO_GRAPH"], ["LV_NO_REUSE"], ["LV_NO_PDL"], ["LV_NO_GRAPH", "LV_NO_PDL"]):
+    # ... nor may the shape of the level-0 search kernel: 8 lanes per query (default), one lane per query, or the
+    # query-per-lane prologue with 8-lane scans (lv_search_coop_kernel)
+    for env in ([], ["LV_NO_GRAPH"], ["LV_NO_REUSE"], ["LV_NO_PDL"], ["LV_NO_GRAPH", "LV_NO_PDL"],
+                ["LV_SEARCH_GROUP=1"], ["LV_SEARCH_GROUP=32"], ["LV_SEARCH_GROUP=32", "LV_NO_GRAPH", "LV_NO_REUSE"]):
         got = run(env)
         for (st0, x0, P0, l0), (st1, x1, P1, l1) in zip(base, got):
             assert st0 == st1 == 0 and len(l0) == len(l1)
