@@ -171,6 +171,11 @@ lv_status lv_measure_reduced(lv_handle h, const double* x, const float* xyz_lida
 lv_status lv_match_all(lv_handle h, const double* x, const float* xyz_lidar, int64_t n,
                        uint8_t* valid, int32_t* nn_idx, float* nn_sqd, float* plane, float* dist,
                        float* g_world);
+/* The neighbours the LAST evaluation of the last lv_correct (or operator call) handed to the plane fit: nn_idx (n x 5,
+ * indices as in lv_match_all, -1 where a query had fewer than five).  lv_match_all always searches afresh; inside an
+ * update, evaluations after the first keep the stored five wherever the exact search provably returns them again
+ * (the reference searches every time, Mapper.cpp:40-56) — this is the window on what the update really used.  */
+lv_status lv_last_neighbours(lv_handle h, int64_t n, int32_t* nn_idx);
 
 /* ---- module boundary: Localizator (include/Headers/Localizator.hpp:24-33) ---------------- */
 lv_status lv_set_state(lv_handle h, const double* x, const double* P);   /* change_x / change_P */

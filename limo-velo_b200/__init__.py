@@ -98,6 +98,7 @@ def lib():
     L.lv_measure.argtypes = [vp, dp, fp, i64, dp, dp, C.POINTER(i64)]
     L.lv_measure_reduced.argtypes = [vp, dp, fp, i64, dp, dp, C.POINTER(i64)]
     L.lv_match_all.argtypes = [vp, dp, fp, i64, C.POINTER(C.c_uint8), i32p, fp, fp, fp, fp]
+    L.lv_last_neighbours.argtypes = [vp, i64, i32p]
     L.lv_set_state.argtypes = [vp, dp, dp]
     L.lv_get_state.argtypes = [vp, dp, dp]
     L.lv_init_state.argtypes = [vp, fp]
@@ -404,6 +405,12 @@ class Localizer:
                                         out["nn_idx"].ctypes.data_as(C.POINTER(C.c_int32)), _f(out["nn_sqd"]),
                                         _f(out["plane"]), _f(out["dist"]), _f(out["g"])), allow=(EMPTY_MAP,))
         out["status"] = st
+        return out
+
+    def last_neighbours(self, n):
+        """map point ids (n x 5) of the neighbours the last evaluation handed to the plane fit"""
+        out = np.zeros((n, 5), np.int32)
+        _check(self.L.lv_last_neighbours(self.h, C.c_int64(n), out.ctypes.data_as(C.POINTER(C.c_int32))), allow=(EMPTY_MAP,))
         return out
 
     # Localizator

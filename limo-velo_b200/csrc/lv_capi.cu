@@ -643,7 +643,7 @@ static lv_status enqueue_update_kernels(lv_context* h, const float* d_xyz, int64
     for (int e = 0; e <= h->prm.MAX_NUM_ITERS; ++e) {            /* i = -1 .. max_iter-1, esekfom.hpp:1634 */
         EventPair ep;
         bool pr;
-        LV_CUDA(launch_measure_timed(h, a, grid, as_job ? 0 : 1, e > 0, (int)(h->update_seq % kNevalsRing), e, pdl));
+        LV_CUDA(launch_measure_timed(h, a, grid, as_job ? 0 : 1, e /* evaluation index: > 0 = reuse + work list */, (int)(h->update_seq % kNevalsRing), e, pdl));
         pr = prof_begin(h, 1, &ep);
         ep.upd = (int)(h->update_seq % kNevalsRing); ep.slot = e;
         LV_CUDA(launch_ieskf_step(h->d_ctrl, h->iprm, h->d_group_rows, partial_groups(grid), h->stream, pdl));
@@ -799,6 +799,29 @@ lv_status lv_match_all(lv_handle h, const double* x, const float* xyz, int64_t n
     return LV_OK;
 }
 
+
+/* the neighbours the LAST evaluation of the last update (or operator call) handed to the plane fit, as map point ids:
+ * after an update with neighbour reuse these are the stored five where lv_reuse_kernel vouched for them and the fresh
+ * search's elsewhere — what lv_match_all (always a fresh search) cannot show */
+__global__ void lv_neighbour_ids_kernel(const int4* nn_a, const int2* nn_b, const float4* arena, int n, int32_t* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 a = nn_a[i];
+    const int2 b = nn_b[i];
+    const int id[5] = {a.x, a.y, a.z, a.w, b.x};
+    for (int k = 0; k < 5; ++k) out[5 * i + k] = (b.x >= 0 && id[k] >= 0) ? __float_as_int(arena[id[k]].w) : -1;
+}
+lv_status lv_last_neighbours(lv_handle h, int64_t n, int32_t* nn_idx) {
+    if (!h || !nn_idx || n <= 0 || n > h->prm.max_points) return LV_ERR_ARG;
+    if (h->map.empty) return LV_EMPTY_MAP;
+    LV_CUDA(cudaSetDevice(h->prm.device));
+    LV_CUDA(ensure(&h->d_nn_idx, 5 * (size_t)h->prm.max_points));
+    lv_neighbour_ids_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->d_nn_a, h->d_nn_b, h->map.arena, (int)n, h->d_nn_idx);
+    LV_CUDA(cudaGetLastError());
+    LV_CUDA(cudaMemcpyAsync(nn_idx, h->d_nn_idx, sizeof(int32_t) * 5 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    LV_CUDA(cudaStreamSynchronize(h->stream));
+    return LV_OK;
+}
 
 /* ---- utilities ------------------------------------------------------------------------------- */
 void* lv_host_alloc(int64_t bytes) {

@@ -114,8 +114,9 @@ int measure_grid(int n);
 /* `probe` (optional) is called on the launching thread before the search (stage 0), after it (1), after the
  * upper-level search (2) and after the fit (3): the profiler records its events there */
 struct MeasureProbe { void (*at)(void* ctx, int stage); void* ctx; };
-/* reuse != 0 (needs a.ref, evaluations after the first of an update): lv_reuse_kernel first, then the search only
- * over the queries it could not vouch for; the probe then sees stage 4 before the reuse kernel */
+/* reuse = index of the evaluation within its update; != 0 (needs a.ref): lv_reuse_kernel first, then the search only
+ * over the queries it could not vouch for; the probe then sees stage 4 before the reuse kernel.  The index also picks
+ * the shape of the level-0 search kernel (search_group() in lv_measure.cu). */
 cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st, const MeasureProbe* probe = nullptr,
                            int reuse = 0, int pdl = 0);
 /* once per update when a.bin_key is set: lv_bin_kernel + radix sort of the (slot, query) pairs */
@@ -124,11 +125,6 @@ size_t bin_sort_tmp_bytes(int64_t max_points);
 cudaError_t launch_ieskf_begin(UpdateCtrl* c, MeasureJob* job, const float* xyz, int n, uint32_t* counters, cudaStream_t st);
 const void* ieskf_begin_kernel_ptr();
 void measure_init();                          /* constant tables; call once before any capture           */
-/* the three kernels of launch_measure() (search instance, search-rings, fit) with their launch shapes, for
- * patching the nodes of a captured update when the map view changes */
-struct MeasureKernelShape { const void* func; unsigned grid, block; };
-enum { kMeasureKernels = 5 };   /* search, search-upper, fit, search over the redo list, reuse */
-void measure_kernel_shapes(const MeasureArgs& a, int grid, MeasureKernelShape out[kMeasureKernels]);
 cudaError_t launch_ieskf_step(UpdateCtrl* c, const IeskfParams& prm, const double* partials, int n_partials,
                               cudaStream_t st, int pdl = 0);
 /* stand-alone reduction of the partials (operator-boundary calls): out[0:144) HTH, [144:156) HTh, [156] Nm */

@@ -870,12 +870,22 @@ int measure_grid(int n) {
 
 void measure_init() { init_pairs(); }
 
-static int search_group() {   /* K1 variant: lanes per query (1, 8) or 32 = lv_search_coop_kernel; LV_SEARCH_GROUP overrides for tuning runs and tests
-                               * (read at every direct launch and when a handle's graph is built, so a test can switch it between handles) */
+/* K1 variant of one launch: lanes per query (1, 4, 8) or 32 = lv_search_coop_kernel.
+ * Measured (profiles/r2_bench_*group*.json, r2_timeline*.txt): 4 lanes per query issue a quarter fewer instructions per query than
+ * 8 (the prologue is shared by eight queries of a warp instead of four) and win when a launch has tens of thousands of queries;
+ * 8 lanes have the shorter chain per query (a bucket of 36 points is one batch of loads instead of two) and win on the short
+ * work lists of late evaluations and on small sweeps.  So the choice follows the number of queries the launch can expect:
+ * all of them in the first evaluation, ~90 % / 45 % / 12 % in evaluations 2 / 3 / 4 of an update with neighbour reuse (cfg1).
+ * LV_SEARCH_GROUP overrides for tuning runs and tests (read at every direct launch and when a handle's graph is built). */
+static int search_group(const MeasureArgs& a, int eval) {
     const char* e = getenv("LV_SEARCH_GROUP");
-    int group = e ? atoi(e) : LV_GROUP;
-    if (group != 1 && group != 8 && group != 32) group = LV_GROUP;
-    return group;
+    if (e) {
+        const int group = atoi(e);
+        if (group == 1 || group == 4 || group == 8 || group == 32) return group;
+    }
+    static const double kRedoShare[4] = {1.0, 0.9, 0.45, 0.12};
+    const double share = (eval > 0 && a.ref) ? kRedoShare[eval < 3 ? eval : 3] : 1.0;
+    return (double)a.n * share >= 40000.0 ? 4 : 8;
 }
 static int search_block(int group) { return group == 32 ? LV_COOP_THREADS : LV_SEARCH_THREADS; }
 static int search_grid(const MeasureArgs& a, int group) {
@@ -883,21 +893,6 @@ static int search_grid(const MeasureArgs& a, int group) {
                                   : (int)(((int64_t)a.n * group + LV_SEARCH_THREADS - 1) / LV_SEARCH_THREADS);
     return sgrid < 1 ? 1 : sgrid;
 }
-template <bool LIST>
-static const void* search_kernel_ptr(int group) {
-    return group == 1 ? (const void*)lv_search_kernel<1, LIST>
-                      : (group == 32 ? (const void*)lv_search_coop_kernel<LIST> : (const void*)lv_search_kernel<8, LIST>);
-}
-void measure_kernel_shapes(const MeasureArgs& a, int grid, MeasureKernelShape out[kMeasureKernels]) {
-    const int group = search_group();
-    out[0].func = search_kernel_ptr<false>(group);
-    out[0].grid = (unsigned)search_grid(a, group); out[0].block = (unsigned)search_block(group);
-    out[1].func = (const void*)lv_search_rings_kernel; out[1].grid = kRingsGrid; out[1].block = 128;
-    out[2].func = (const void*)lv_fit_kernel; out[2].grid = (unsigned)(grid + (a.prep ? 1 : 0)); out[2].block = kMeasureThreads;
-    out[3].func = search_kernel_ptr<true>(group); out[3].grid = out[0].grid; out[3].block = out[0].block;
-    out[4].func = (const void*)lv_reuse_kernel; out[4].grid = (unsigned)((a.n + 127) / 128 > 0 ? (a.n + 127) / 128 : 1); out[4].block = 128;
-}
-
 /* <<<>>> with the programmatic-dependent-launch attribute when `pdl` (see pdl_wait above) */
 template <class... Params, class... Args>
 static cudaError_t launch_k(void (*kernel)(Params...), unsigned grid, unsigned block, cudaStream_t st, bool pdl, Args... args) {
@@ -918,13 +913,14 @@ static void launch_search(const MeasureArgs& a, int group, int sgrid, cudaStream
     switch (group) {
         case 1: launch_k(lv_search_kernel<1, LIST>, sgrid, LV_SEARCH_THREADS, st, pdl, a); break;
         case 32: launch_k(lv_search_coop_kernel<LIST>, sgrid, LV_COOP_THREADS, st, pdl, a); break;
+        case 4: launch_k(lv_search_kernel<4, LIST>, sgrid, LV_SEARCH_THREADS, st, pdl, a); break;
         default: launch_k(lv_search_kernel<8, LIST>, sgrid, LV_SEARCH_THREADS, st, pdl, a); break;
     }
 }
 
 cudaError_t launch_measure(const MeasureArgs& a, int grid, cudaStream_t st, const MeasureProbe* probe, int reuse, int pdl) {
     init_pairs();
-    const int group = search_group();
+    const int group = search_group(a, reuse);          /* reuse = index of the evaluation within its update */
     const int sgrid = search_grid(a, group);
     /* work-list length, a spare word, redo-list length; inside an update with pdl the kernels
      * reset them themselves (begin kernel, fit kernel) so that every node of the update is a kernel */
