@@ -243,6 +243,15 @@ LV_HD bool level0_scan(const VoxelMapView& m, float gx, float gy, float gz, floa
         const float4* p = m.arena + bstart;
         const uint32_t n = bcount, step = (uint32_t)Grp::size;
         uint32_t j = (uint32_t)Grp::lane();
+        if (Grp::size <= 4) {                        /* few lanes per query: eight loads in flight per lane, or a 36-point bucket is three round trips */
+            for (; j + 7 * step < n; j += 8 * step) {
+                float4 q[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) q[u] = load_point(p + j + (uint32_t)u * step);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) top5_insert(loc, sq_dist(gx, gy, gz, q[u].x, q[u].y, q[u].z), (int)(bstart + j + (uint32_t)u * step));
+            }
+        }
         for (; j + 3 * step < n; j += 4 * step) {   /* four independent 16-byte loads in flight per lane */
             const float4 q0 = load_point(p + j), q1 = load_point(p + j + step), q2 = load_point(p + j + 2 * step),
                          q3 = load_point(p + j + 3 * step);
