@@ -6,7 +6,10 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as G
 lv = G.load_package(); O = G.load_oracle()
-for sort_queries in (0, 1):
+for sort_queries, group in ((0, None), (0, "4"), (0, "32"), (0, "1"), (1, None)):    # every shape of the level-0 search
+    os.environ.pop("LV_SEARCH_GROUP", None)
+    if group:
+        os.environ["LV_SEARCH_GROUP"] = group
     prm = lv.params_from_yaml(os.path.join(lv.CONFIG_DIR, "xaloc.yaml"), max_map_points=1 << 17, max_points=1 << 13, sort_queries=sort_queries)
     world = lv.SynthWorld(20260924, 40000)
     truth = world.pose(10.0, prm)
@@ -30,10 +33,11 @@ for sort_queries in (0, 1):
         st, x, P, logs = loc.correct(sweep)
         st_o, x_o, P_o, logs_o = om.update_iterated(x_prop, P0, oprm, sweep)
         assert st == st_o == 0 and len(logs) == len(logs_o) and np.abs(x - x_o).max() < 1e-7
+        assert loc.last_neighbours(len(sweep)).shape == (len(sweep), 5)
         loc.map_add_last_sweep(True)
         om.add(om.match_all(x, oprm, sweep)["g"], downsample=True)
         loc.map_status()
         assert abs(loc.map_size() - len(om.points())) <= 2
         loc.propagate_device(np.tile([0.0, 0.0, 9.8], (4, 1)), np.zeros((4, 3)), np.full(4, 1e-3))
     loc.close()
-    print("sanitize target: sort_queries=%d ok" % sort_queries, flush=True)
+    print("sanitize target: sort_queries=%d search group %s ok" % (sort_queries, group or "default"), flush=True)
