@@ -77,6 +77,9 @@ def test_argument_errors(lv):
     xyz, t = (C.c_float * 3)(), (C.c_double * 1)()
     assert L.lv_pointcloud2_to_points(9, C.byref(lay), buf, C.c_int64(1), C.c_uint64(0), 0, 1, C.c_double(0.1), xyz, t, None, None) == lv.ERR_ARG
     assert L.lv_time_sort_indices(None, C.c_int64(0), None) == lv.ERR_ARG
+    # inspection and tick entry points added in round 2
+    assert L.lv_last_neighbours(None, C.c_int64(1), None) == lv.ERR_ARG
+    assert L.lv_map_add_last_sweep(None, 1) == lv.ERR_ARG and L.lv_map_add_device(None, None, C.c_int64(0), 1) == lv.ERR_ARG
 
 
 def test_yaml_reader_matches_pyyaml(lv):
