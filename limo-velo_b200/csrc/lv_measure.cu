@@ -586,6 +586,14 @@ __global__ void __launch_bounds__(kMeasureThreads, 4) lv_fit_kernel(const Measur
         if (!done) prepare_block(a.prep);
         pdl_wait();
         pdl_trigger();
+#ifdef LV_STEP_TIMING
+        if (threadIdx.x < 32) {   /* tuning build: how many queries this evaluation searched again, how many went to the ring search */
+            unsigned v = a.hard_count[4 + threadIdx.x];
+            for (int s_ = 16; s_ > 0; s_ >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s_);
+            if (threadIdx.x == 0) { g_tl[2][a.ctrl->n_evals & 7][6] = v; g_tl[2][a.ctrl->n_evals & 7][7] = a.hard_count[2]; }
+        }
+        __syncthreads();
+#endif
         /* the searches of this evaluation are over: reset their counters for the next one */
         if (threadIdx.x < kCounters) a.hard_count[threadIdx.x] = 0u;
         return;

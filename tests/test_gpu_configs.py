@@ -28,14 +28,23 @@ def _check_update(loc, om, oprm, x_prop, P0, sweep, O, min_matches):
     st, x, P, logs = loc.correct(sweep)
     st_o, x_o, P_o, logs_o = om.update_iterated(x_prop, P0, oprm, sweep)
     assert st == st_o == 0 and len(logs) == len(logs_o)
-    for k, (a, b) in enumerate(zip(logs, logs_o)):
-        assert a["n_matches"] == b["n_matches"] > min_matches, (k, a["n_matches"], b["n_matches"])
-        assert np.abs(a["HTH"] - b["HTH"]).max() <= (1e-12 if k == 0 else 1e-8) * np.abs(b["HTH"]).max()
-        assert np.abs(a["dx"] - b["dx"]).max() < (1e-9 if k == 0 else 1e-7), (k, np.abs(a["dx"] - b["dx"]).max())
-    assert np.abs(x - x_o).max() < 1e-7
-    assert np.abs(P - P_o).max() <= 1e-6 * np.abs(P_o).max()
+    # per evaluation at the GPU's iterate: Nm equal, HTH 1e-12, dx 1e-9; queries whose 5th and 6th neighbours are exactly
+    # equidistant are taken apart explicitly there (test_gpu_fullsize.check_every_evaluation) and counted
     from test_gpu_fullsize import check_every_evaluation
-    check_every_evaluation(O, om, oprm, x_prop, P0, sweep, logs, loc)     # per evaluation at the GPU's iterate: Nm equal, HTH 1e-12, dx 1e-9
+    ties = check_every_evaluation(O, om, oprm, x_prop, P0, sweep, logs, loc)
+    loc.set_state(x, P)
+    # against the free-running oracle chain: exact counts and tight bars unless such a tie sent the two chains different ways
+    for k, (a, b) in enumerate(zip(logs, logs_o)):
+        assert a["n_matches"] > min_matches
+        if ties == 0:
+            assert a["n_matches"] == b["n_matches"], (k, a["n_matches"], b["n_matches"])
+            assert np.abs(a["HTH"] - b["HTH"]).max() <= (1e-12 if k == 0 else 1e-8) * np.abs(b["HTH"]).max()
+            assert np.abs(a["dx"] - b["dx"]).max() < (1e-9 if k == 0 else 1e-7), (k, np.abs(a["dx"] - b["dx"]).max())
+        else:
+            assert abs(a["n_matches"] - b["n_matches"]) <= ties + 4
+            assert np.abs(a["dx"] - b["dx"]).max() < 2e-5
+    assert np.abs(x - x_o).max() < (1e-7 if ties == 0 else 2e-5)
+    assert np.abs(P - P_o).max() <= (1e-6 if ties == 0 else 1e-5) * np.abs(P_o).max()
     return x, logs
 
 
@@ -44,8 +53,13 @@ def _check_points(loc, om, oprm, x_prop, sweep):
     ref = om.match_all(x_prop, oprm, sweep)
     inside = np.isfinite(got["nn_sqd"][:, 4])
     assert not (ref["nn_sqd"][~inside, 4].astype(np.float64) < oprm.max_dist_plane ** 2).any()
-    assert (got["nn_sqd"][inside] == ref["nn_sqd"][inside]).all()
-    assert (got["valid"] == ref["valid"]).all() and (got["plane"] == ref["plane"]).all() and (got["dist"] == ref["dist"]).all()
+    assert (got["nn_sqd"][inside] == ref["nn_sqd"][inside]).all()          # the five distances: bit for bit, ties or not
+    # plane, distance, accept bit: bit for bit too — except for a query whose 5th and 6th neighbours are exactly equidistant,
+    # where the two searches may hold different fifth points (same distance, other coordinates)
+    differ = np.nonzero((got["valid"] != ref["valid"]) | (got["plane"] != ref["plane"]).any(1) | (got["dist"] != ref["dist"]))[0]
+    if len(differ):
+        from test_gpu_fullsize import boundary_ties
+        assert len(differ) <= 4 and len(boundary_ties(om, ref["g"][differ])) == len(differ), differ
     return got
 
 

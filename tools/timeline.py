@@ -5,8 +5,9 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as G, bench
 lv = G.load_package()
-prm = lv.params_from_yaml(lv.CONFIG_DIR + "/xaloc.yaml", max_map_points=bench.MAP_POINTS + 4 * 65536, max_points=65536)
-world, mp, sweeps, x_props, truths = bench.make_scene(lv, 0, n_sweeps=2, prm=prm)
+CFG = os.environ.get("LV_TIMELINE_CFG", "cfg1")             # any of bench.CONFIGS but cfg4
+prm = bench.config_params(lv, CFG)
+world, mp, sweeps, x_props, truths = bench.make_scene(lv, 0, n_sweeps=2, prm=prm, cfg=CFG)
 prm.sort_queries = int(os.environ.get("LV_TIMELINE_SORT", "0"))
 x0, P0 = lv.init_state_host(prm)
 loc = lv.Localizer(prm); loc.map_build(mp)
@@ -19,7 +20,7 @@ for it in range(6):
     loc.synchronize()
     loc.L.lv_debug_timeline(buf)            # reset
     pr = (ctypes.c_ulonglong * 2)(); loc.L.lv_debug_probes(pr)
-    loc.correct_device(d[it % 2], 65536)
+    loc.correct_device(d[it % 2], len(sweeps[it % 2]))
     loc.synchronize()
     loc.L.lv_debug_timeline(buf)
     loc.L.lv_debug_probes(pr); print("hash probes in this update:", pr[0])
@@ -32,4 +33,4 @@ for it in range(6):
         for k in (1, 2, 3, 4, 5):
             if t[0][e][k] < 1.8e19:
                 row.append(f"{names[k]} {1e-3 * (t[0][e][k] - t0):6.1f}/{1e-3 * (t[1][e][k] - t0):6.1f}..{1e-3 * (t[3][e][k] - t0):6.1f}/{1e-3 * (t[2][e][k] - t0):6.1f}|{1e-3 * (t[4][e][k] - t0):6.1f}")
-        print(f"  eval {e}: " + "  ".join(row))
+        print(f"  eval {e}: " + "  ".join(row) + f"   [searched again {int(t[2][e][7])}, ring search {int(t[2][e][6])}]")
