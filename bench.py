@@ -196,6 +196,19 @@ def oracle_params(O, prm):
                          limits=list(prm.LIMITS))
 
 
+_OUT_FD = None
+
+
+def _emit(line):
+    """The ONE JSON line, on the stdout this process was started with.  Everything else that writes to fd 1 while the bench runs
+    (NCCL's version banner under torchrun, the reference ikd-Tree's thread messages) has been pointed at stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _OUT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_OUT_FD, data)
+
+
 class _StdoutToStderr:
     """The reference's ikd-Tree announces its rebuild thread on C stdout ("Multi thread started");
     keep this process' stdout clean for the ONE JSON line by pointing fd 1 at fd 2 meanwhile."""
@@ -275,7 +288,7 @@ def run_reference(args, rank, world_size):
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "host_cpu_count": ncores,
             "product_library_loaded": any("liblimovelo_b200" in l for l in open("/proc/self/maps"))}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def run_native(args, rank, local_rank, world_size):
@@ -547,7 +560,7 @@ def run_native(args, rank, local_rank, world_size):
             "final_position_error_m": pose_err,
             "clocks": clock_info,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     for pb in pinned:
         pb.free()
     loc.close()
@@ -716,7 +729,7 @@ def run_strong(args, rank, local_rank, world_size):
                                "CUDA events fork/join over all streams of the rank, max over ranks"},
                 "gpu_launches": int(round(red["launches"])), "sequences_total": n_seq, "sequences_per_gpu": len(mine),
                 "e2e_wall_ms_per_step": 1e3 * e2e_wall / args.steps, "final_position_error_m": err, "clocks": clock_info}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     for loc in locs:
         loc.close()
     if world_size > 1:
@@ -766,6 +779,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    global _OUT_FD
+    sys.stdout.flush()
+    _OUT_FD = os.dup(1)             # keep the real stdout for the JSON line only
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world_size)
     elif args.config == "cfg4":
