@@ -512,7 +512,11 @@ def run_native(args, rank, local_rank, world_size):
         # lv_ieskf_step_kernel takes about as long per evaluation but moves no per-point bytes: it is ~12 us of
         # dependent fp64 23x23 algebra in one block; its time is listed in kernel_ms.
         dominant = "lv_search_kernel"
-        achieved = ALGO_BYTES_PER_POINT * n / (k_ms[dominant] * 1e-3) / 1e9 if k_ms[dominant] > 0 else 0.0
+        # ... timed on the launches that search EVERY query (the first evaluation of each update): later evaluations only
+        # search what the reuse test hands back, their launches are shorter for doing less, and 72 B x n is not their traffic
+        first_ms = prof["search_first_ms"] / max(1, prof["search_first_launches"])
+        k_ms["lv_search_kernel_first_evaluation"] = first_ms
+        achieved = ALGO_BYTES_PER_POINT * n / (first_ms * 1e-3) / 1e9 if first_ms > 0 else 0.0
         traffic, traffic_src = None, None
         try:                                                        # dram bytes per launch from the committed ncu --set full capture
             if cfg != "cfg1" or args.sort_queries or args.voxel:
@@ -550,7 +554,8 @@ def run_native(args, rank, local_rank, world_size):
                           "solve_launches": prof["solve_launches"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                          "frac": achieved / peak_gbs, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "kernel": dominant, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_POINT * n},
+                         "kernel": dominant, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_POINT * n,
+                         "launches_timed": "first evaluation of every update (all %d queries searched): %d launches, %.2f us each (CUDA events, live pass)" % (n, prof["search_first_launches"], 1e3 * first_ms)},
             "cpu_baseline": cpu,
             "per_sweep": per_sweep,
             "map_update": {"lv_map_add_ms": 1e3 * min(t_add), "points_added": n, "map_points": loc.map_size(),

@@ -110,6 +110,9 @@ typedef struct lv_profile {
     double search_upper_ms;   /* lv_search_rings_kernel: the queries level 0 cannot certify */
     double fit_ms;            /* lv_fit_kernel: plane fit, Jacobian rows, normal equations  */
     double reuse_ms;          /* lv_reuse_kernel: neighbours carried over from the previous evaluation */
+    double search_first_ms;   /* the part of search_ms spent in FIRST evaluations: those launches search every query of the
+                               * sweep (later ones only the queries the reuse test handed back)                  */
+    int64_t search_first_launches;
 } lv_profile;
 
 /* ------------------------------------------------------------------------------------------ */

@@ -50,7 +50,7 @@ class Profile(C.Structure):
                 ("measure_launches", C.c_int64), ("solve_launches", C.c_int64), ("build_launches", C.c_int64),
                 ("total_launches", C.c_int64), ("idle_ms", C.c_double), ("idle_launches", C.c_int64),
                 ("search_ms", C.c_double), ("search_upper_ms", C.c_double), ("fit_ms", C.c_double),
-                ("reuse_ms", C.c_double)]
+                ("reuse_ms", C.c_double), ("search_first_ms", C.c_double), ("search_first_launches", C.c_int64)]
 
 
 def build(verbose=False):

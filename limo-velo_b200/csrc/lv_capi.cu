@@ -127,7 +127,10 @@ static lv_status drain_events(lv_context* h) {
         const bool idle = e.upd >= 0 && e.slot >= h->h_nevals[e.upd % kNevalsRing];
         if (idle) { h->prof.idle_ms += ms; h->prof.idle_launches++; }
         else if (e.kind == 0) { h->prof.measure_ms += ms; h->prof.measure_launches++; }
-        else if (e.kind == 3) { h->prof.search_ms += ms; h->prof.measure_ms += ms; h->prof.measure_launches++; }
+        else if (e.kind == 3) {
+            h->prof.search_ms += ms; h->prof.measure_ms += ms; h->prof.measure_launches++;
+            if (e.slot <= 0) { h->prof.search_first_ms += ms; h->prof.search_first_launches++; }
+        }
         else if (e.kind == 4) { h->prof.search_upper_ms += ms; h->prof.measure_ms += ms; }
         else if (e.kind == 5) { h->prof.fit_ms += ms; h->prof.measure_ms += ms; }
         else if (e.kind == 6) { h->prof.reuse_ms += ms; h->prof.measure_ms += ms; }
