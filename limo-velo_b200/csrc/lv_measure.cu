@@ -37,7 +37,11 @@ __device__ long long g_step_clk[64];
 #ifdef __CUDA_ARCH__
 #define LV_CK(k) do { if (threadIdx.x == 0) g_step_clk[k] = clock64(); } while (0)
 #define LV_TK(k) do { g_step_clk[k] = clock64(); } while (0)
+#define LV_FK(k) do { if (threadIdx.x == 0 && blockIdx.x == 1) g_step_clk[k] = clock64(); } while (0)
 #endif
+#endif
+#ifndef LV_FK
+#define LV_FK(k)
 #endif
 
 #include <cub/device/device_radix_sort.cuh>
@@ -102,7 +106,7 @@ __device__ __forceinline__ JobView job_view(const MeasureArgs& a) {
     return j;
 }
 
-#define LV_ROW_STRIDE (kMeasureThreads + 1)   /* +1 double: 13 row-columns land in distinct banks */
+#define LV_ROW_STRIDE (kMeasureThreads + 4)   /* 132 doubles = 4 (mod 16): the 8 x 4 fragment loads of the fold below are conflict-free */
 #define LV_SEARCH_THREADS 128
 #define LV_GROUP 8                              /* lanes per query in K1 (LV_SEARCH_GROUP=1|8 overrides) */
 
@@ -600,7 +604,9 @@ __global__ void __launch_bounds__(kMeasureThreads, 4) lv_fit_kernel(const Measur
     }
 
     __shared__ Frame s_frame;
-    __shared__ double s_rows[13 * LV_ROW_STRIDE];
+    __shared__ double s_rows[16 * LV_ROW_STRIDE];   /* 13 columns of the tile's rows (12 of H, then h), padded to 16 with zeros */
+    __shared__ double s_part[4 * 192];              /* per warp: its share of the three 8 x 8 tiles of [H h]^T [H h] */
+    for (int i = threadIdx.x; i < 3 * LV_ROW_STRIDE; i += kMeasureThreads) s_rows[13 * LV_ROW_STRIDE + i] = 0.0;
 
     {   /* the frame of the current iterate: written by the step kernel, broadcast via smem */
         const uint32_t* src = reinterpret_cast<const uint32_t*>(&a.ctrl->frame);
@@ -617,10 +623,12 @@ __global__ void __launch_bounds__(kMeasureThreads, 4) lv_fit_kernel(const Measur
         if (bid < jb.n_tiles && i < jb.n)
             rt_apply(s_frame.lidar_to_world, jb.xyz[3 * i], jb.xyz[3 * i + 1], jb.xyz[3 * i + 2], g0);
     }
+    LV_FK(56);
     pdl_wait();                 /* the neighbour lists */
     pdl_trigger();
     LV_TL_WORK(a.ctrl, 4);
     if (done) return;
+    LV_FK(57);
 
     double acc = 0.0;
     int count = 0;
@@ -653,6 +661,7 @@ __global__ void __launch_bounds__(kMeasureThreads, 4) lv_fit_kernel(const Measur
                 orig[0] = __float_as_int(q0.w); orig[1] = __float_as_int(q1.w); orig[2] = __float_as_int(q2.w);
                 orig[3] = __float_as_int(q3.w); orig[4] = __float_as_int(q4.w);
                 for (int k = 0; k < 5; ++k) dsq[k] = sq_dist(g[0], g[1], g[2], q[k][0], q[k][1], q[k][2]);
+                LV_FK(58);
                 canonical_neighbour_order(q, dsq, orig);             /* equidistant neighbours: the reference's (distance, x) order */
                 /* Plane.cpp:36-43: 5 neighbours and the farthest closer than MAX_DIST_PLANE */
                 if ((double)d4 < a.gate_d2) {
@@ -680,26 +689,45 @@ __global__ void __launch_bounds__(kMeasureThreads, 4) lv_fit_kernel(const Measur
                 a.rows[13 * (size_t)i + 12] = chosen ? hval : 0.0;
             }
         }
+        LV_FK(59);
         /* stage the row (zeros when rejected), fold the tile into the block's 90 sums */
 #pragma unroll
         for (int k = 0; k < 12; ++k) s_rows[k * LV_ROW_STRIDE + tid] = chosen ? row[k] : 0.0;
         s_rows[12 * LV_ROW_STRIDE + tid] = chosen ? hval : 0.0;
         count += __syncthreads_count(chosen ? 1 : 0);
-        if (tid < 90) {
-            const double* ra = s_rows + c_pair_a[tid] * LV_ROW_STRIDE;
-            const double* rb = s_rows + c_pair_b[tid] * LV_ROW_STRIDE;
-            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-#pragma unroll 8
-            for (int k = 0; k < kMeasureThreads; k += 4) {
-                s0 += ra[k] * rb[k];
-                s1 += ra[k + 1] * rb[k + 1];
-                s2 += ra[k + 2] * rb[k + 2];
-                s3 += ra[k + 3] * rb[k + 3];
+        LV_FK(60);
+        {
+            /* The tile's 13 x 13 Gram matrix on the fp64 tensor cores (mma.m8n8k4: D = A B + C, A 8x4, B 4x8): 16 x 16 with
+             * the padding, three 8 x 8 tiles (00, 01, 11 — it is symmetric), each warp a quarter of the 128 rows.  A lane's A
+             * fragment of column-tile I is element (column I*8 + lane/4, row k0 + lane%4) and the B fragment of column-tile J
+             * is the same expression with J: two loads feed three MMAs of 256 multiply-adds each.  (The scalar fold — 90
+             * threads x 128 x two 8-byte shared loads per multiply-add — spent 4 400 cycles per tile waiting for the four
+             * resident blocks' 6 000 shared-memory wavefronts; clock64, tools/step_timing.py.) */
+            const int lane = tid & 31, w = tid >> 5;
+            const double* f0 = s_rows + (lane >> 2) * LV_ROW_STRIDE + 32 * w + (lane & 3);
+            const double* f1 = f0 + 8 * LV_ROW_STRIDE;
+            double c00a = 0.0, c00b = 0.0, c01a = 0.0, c01b = 0.0, c11a = 0.0, c11b = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+                const double a0 = f0[4 * ks], a1 = f1[4 * ks];
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c00a), "+d"(c00b) : "d"(a0), "d"(a0));
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c01a), "+d"(c01b) : "d"(a0), "d"(a1));
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c11a), "+d"(c11b) : "d"(a1), "d"(a1));
             }
-            acc += (s0 + s1) + (s2 + s3);
+            double* pt = s_part + w * 192 + (lane >> 2) * 8 + 2 * (lane & 3);   /* C fragment: row lane/4, columns 2 (lane%4), +1 */
+            pt[0] = c00a; pt[1] = c00b;
+            pt[64] = c01a; pt[65] = c01b;
+            pt[128] = c11a; pt[129] = c11b;
+        }
+        __syncthreads();
+        if (tid < 90) {   /* entry (a, b), a <= b: tile 00 / 01 / 11; the warps' shares in warp order */
+            const int pa = c_pair_a[tid], pb = c_pair_b[tid];
+            const int idx = (pa < 8 ? (pb < 8 ? 0 : 64) : 128) + (pa & 7) * 8 + (pb & 7);
+            acc += (s_part[idx] + s_part[192 + idx]) + (s_part[384 + idx] + s_part[576 + idx]);
         }
         __syncthreads();
     }
+    LV_FK(61);
     double* out = a.partials + (size_t)bid * kPartialStride;
     if (tid < 90) out[tid] = acc;
     if (tid == 90) out[90] = (double)count;
@@ -719,6 +747,7 @@ __global__ void __launch_bounds__(kMeasureThreads, 4) lv_fit_kernel(const Measur
         if (s_last) a.group_tickets[grp] = 0u;          /* nobody else touches it before the next evaluation */
     }
     __syncthreads();
+    LV_FK(62);
     if (s_last) {
         __threadfence();
         if (tid < 91) {
@@ -731,6 +760,7 @@ __global__ void __launch_bounds__(kMeasureThreads, 4) lv_fit_kernel(const Measur
             a.group_rows[(size_t)grp * kPartialStride + tid] = sum;
         }
     }
+    LV_FK(63);
     LV_TL_END(4);
 }
 
