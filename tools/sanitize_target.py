@@ -6,7 +6,10 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import __graft_entry__ as G
 lv = G.load_package(); O = G.load_oracle()
-for sort_queries, group in ((0, None), (0, "4"), (0, "32"), (0, "1"), (1, None)):    # every shape of the level-0 search
+VARIANTS = ((0, None), (0, "4"), (0, "32"), (0, "1"), (1, None))                    # every shape of the level-0 search
+if os.environ.get("LV_SANITIZE_QUICK"):
+    VARIANTS = ((0, "4"), (1, None))
+for sort_queries, group in VARIANTS:
     os.environ.pop("LV_SEARCH_GROUP", None)
     if group:
         os.environ["LV_SEARCH_GROUP"] = group
